@@ -1,0 +1,98 @@
+/* mpinn_b200.h -- C ABI of the B200-native PINN train-step library (libmpinn_b200.so).
+ *
+ * The reference (multipinn) is pure Python on PyTorch and has no FFI of its own; the "operator
+ * API" this library sits behind is the set of Python call signatures on its hot path.  Each
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * tree).  The Python host (multipinn_b200/_lib.py) binds these with ctypes; see INTEGRATION.md
+ * for the stub a multipinn maintainer would add.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless it says "host"; all arrays are fp32,
+ * dense, row-major; `stream` is a cudaStream_t passed as void*; every call is asynchronous on
+ * that stream and returns 0 on success or a non-zero code with a message available through
+ * mpinn_last_error().  No entry point allocates device memory.
+ *
+ * Jet channels of a network output, per point:  0 = value, 1..d = d/dx_i, d+1..2d = d2/dx_i^2;
+ * J = 1 + order*d for order in {0,1,2}.
+ */
+#ifndef MPINN_B200_H
+#define MPINN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPINN_ABI_VERSION 1
+#define MPINN_MAX_OPS 64
+
+enum { MPINN_OP_LINEAR = 0, MPINN_OP_FOURIER = 1 };
+enum { MPINN_ACT_NONE = 0, MPINN_ACT_SINE = 1, MPINN_ACT_GELU = 2 };
+enum { MPINN_FLAG_SAVE_SKIP = 1, MPINN_FLAG_ADD_SKIP = 2 };
+enum { MPINN_ENGINE_AUTO = 0, MPINN_ENGINE_FFMA = 1, MPINN_ENGINE_TCGEN05 = 2 };
+
+/* One layer of the network "program" (host struct, passed by pointer to host memory).
+ *   LINEAR : z = W h + b (+ skip), a = act(z); W is [out_dim,in_dim] at params+w_off, b at params+b_off
+ *            (the nn.Linear layout: reference neural_network/feedforward_neural_network.py:28-37)
+ *   FOURIER: a = [sin(xB), cos(xB)], B is [in_dim,out_dim/2] at params+w_off
+ *            (reference neural_network/fourier_features.py:30-40)
+ *   flags  : SAVE_SKIP remembers this op's input; ADD_SKIP adds it before the activation
+ *            (reference neural_network/light_residual_block.py:33-38)                       */
+typedef struct mpinn_op {
+  int32_t kind, in_dim, out_dim, w_off, b_off, act, flags, reserved;
+} mpinn_op_t;
+
+int mpinn_abi_version(void);
+const char* mpinn_last_error(void);
+
+/* Bytes of device scratch the forward pass needs to stash pre-activations for the reverse pass,
+ * and bytes of workspace the reverse pass needs (per-CTA partial parameter gradients). */
+size_t mpinn_stash_bytes(const mpinn_op_t* ops_host, int n_ops, int d, int order, int64_t n_points);
+size_t mpinn_backward_workspace_bytes(const mpinn_op_t* ops_host, int n_ops, int64_t n_params);
+/* Bytes of the packed-weight buffer (transposed / padded / hi-lo split copies of the weights). */
+size_t mpinn_packed_bytes(const mpinn_op_t* ops_host, int n_ops);
+
+/* Re-pack the flat parameter vector into the kernels' operand layouts.  Call once after every
+ * parameter update (one small launch). */
+int mpinn_pack_params(const mpinn_op_t* ops_host, int n_ops, const float* params, void* packed,
+                      void* stream);
+
+/* Forward jets of the whole network.
+ * Replaces `model(arg)` + the nested `grad(u,arg)` sweeps:
+ *   reference neural_network/feedforward_neural_network.py:39-52 (FNN.forward),
+ *   residual_neural_network.py:114-126, fourier_features.py:73-76, condition/diff.py:25-47.
+ *   x    [n,d]      collocation points
+ *   out  [J,n,o]    jets of the o network outputs (o = out_dim of the last op)
+ *   stash           mpinn_stash_bytes() bytes, or NULL for a value-only/inference pass      */
+int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params,
+                      const void* packed, const float* x, int64_t n, int d, int order, float* out,
+                      void* stash, int engine, void* stream);
+
+/* Reverse pass: parameter gradient of a scalar loss given dL/d(out jets).
+ * Replaces `loss.backward()` through the double-backward graph (reference trainer/trainer.py:141).
+ *   dout    [J,n,o]  gradient w.r.t. the forward's `out`
+ *   dparams [P]      ACCUMULATED into (+=); P = number of floats in `params`
+ *   dx      [n,d]    written if non-NULL (gradient w.r.t. the points), else skipped          */
+int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* params,
+                       const void* packed, const float* x, int64_t n, int d, int order,
+                       const float* dout, const void* stash, float* dparams, int64_t n_params,
+                       float* dx, void* workspace, size_t workspace_bytes, int engine,
+                       void* stream);
+
+/* sum_i r[i*stride]^2 added into *accum (device scalar).
+ * Replaces `torch.sum(r**2)` (reference PINN/PINN.py:59,95,123). */
+int mpinn_sumsq(const float* r, int64_t n, int64_t stride, float* accum, void* stream);
+
+/* Fused Adam over flat buffers; g is multiplied by grad_scale first (1/world for DP).
+ * Replaces `optimizer.step()` with torch.optim.Adam(lr, betas, eps) (reference
+ * trainer/trainer.py:150,235,335; examples/<name>/configs/config.yaml:41-44).  `step` is the
+ * 1-based step count of this update. */
+int mpinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    int64_t n, int64_t step, float lr, float beta1, float beta2, float eps,
+                    float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPINN_B200_H */

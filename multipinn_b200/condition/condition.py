@@ -1,0 +1,122 @@
+"""``Condition`` / ``ConditionExtra`` with the reference's interface
+(reference ``multipinn/condition/condition.py:6-215``): a residual callable bound to a geometry and
+a point generator, sliced per batch / per rank.
+
+Addition over the reference: each (condition, model) pair keeps a ``ResidualPlan`` recording which
+jet order every ``model(arg)`` call inside the residual function needs.  It is filled by the probe
+evaluation the reference already performs in ``init_output_len`` and consulted on every later call,
+so the fused forward computes exactly the derivative channels the residual will ask for.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Callable, List, Union
+
+import torch
+
+from ..jet import ResidualPlan, UnsupportedDerivative, use_plan
+
+
+class Condition:
+    def __init__(self, function: Callable, geometry) -> None:
+        self.function = function
+        self.geometry = geometry
+        self.generator = None
+        self.points = None
+        self.batch_size = None
+        self.batch_points = None
+        self.output_len = None
+        self._plans = weakref.WeakKeyDictionary()
+
+    # -- jet-order bookkeeping -------------------------------------------------------------
+    def plan_for(self, model) -> ResidualPlan:
+        try:
+            plan = self._plans.get(model)
+        except TypeError:  # unhashable / non-weakrefable stand-ins (mocks)
+            return None
+        if plan is None:
+            plan = ResidualPlan()
+            self._plans[model] = plan
+        return plan
+
+    def _call(self, model, *args):
+        with use_plan(self.plan_for(model)):
+            return self.function(model, *args)
+
+    # -- reference interface ---------------------------------------------------------------
+    def update_points(self, model=None) -> None:
+        self.points = self.generator.generate(self, model)
+
+    def select_batch(self, i: int) -> None:
+        start = i * self.batch_size
+        self.batch_points = self.points[start:start + self.batch_size]
+
+    def get_residual(self, model) -> List[torch.Tensor]:
+        return self._call(model, self.batch_points)
+
+    def get_residual_fn(self, model) -> Callable:
+        def residual(arg):
+            return self._call(model, arg)
+
+        return residual
+
+    def set_batching(self, num_batches: int) -> None:
+        assert self.generator.n_points % num_batches == 0, "Points must divide evenly into batches"
+        self.batch_size = self.generator.n_points // num_batches
+
+    def _probe_point(self, model) -> torch.Tensor:
+        device = next(model.parameters()).device
+        low = torch.as_tensor(self.geometry.bbox[0], dtype=torch.float32, device=device)
+        high = torch.as_tensor(self.geometry.bbox[1], dtype=torch.float32, device=device)
+        return ((low + high) * 0.5).reshape(1, -1).requires_grad_()
+
+    def init_output_len(self, model) -> None:
+        """Evaluate the residual once at the bbox centre: sets ``output_len`` (as the reference does)
+        and, as a side effect, fills the jet-order plan and validates that the residual only uses
+        derivatives the jet path provides."""
+        residuals = self.get_residual_fn(model)(self._probe_point(model))
+        self.output_len = len(residuals)
+        for k, r in enumerate(residuals):
+            if isinstance(r, torch.Tensor) and bool(torch.isnan(r).any()):
+                raise UnsupportedDerivative(
+                    f"residual component {k} of {getattr(self.function, '__name__', self.function)} is NaN at "
+                    "the probe point: it most likely uses a mixed second derivative, which the fused jet "
+                    "path does not compute (only d2/dx_i^2).")
+
+
+class ConditionExtra(Condition):
+    """Condition whose residual takes auxiliary per-point data, e.g. boundary normals
+    (reference ``condition/condition.py:117-215``)."""
+
+    def __init__(self, function: Callable, geometry, data_gen: List[Union[str, Callable]]):
+        super().__init__(function, geometry)
+        data_gen = list(data_gen)
+        if "normals" in data_gen:
+            assert hasattr(geometry, "boundary_normal"), "Geometry must support normal vectors"
+            data_gen[data_gen.index("normals")] = ConditionExtra.generator_for_normals(geometry)
+        self.data_gen = lambda points: tuple(fn(points) for fn in data_gen)
+        self.data = None
+        self.batch_data = None
+
+    @staticmethod
+    def generator_for_normals(geometry) -> Callable:
+        return lambda points: torch.tensor(
+            geometry.boundary_normal(points.detach().cpu().numpy()), device=points.device)
+
+    def update_points(self, model=None) -> None:
+        self.points = self.generator.generate(self, model)
+        self.data = self.data_gen(self.points)
+
+    def select_batch(self, i: int) -> None:
+        start = i * self.batch_size
+        self.batch_points = self.points[start:start + self.batch_size]
+        self.batch_data = self.data[start:start + self.batch_size]
+
+    def get_residual(self, model) -> List[torch.Tensor]:
+        return self._call(model, self.batch_points, self.batch_data)
+
+    def get_residual_fn(self, model) -> Callable:
+        def residual(arg):
+            return self._call(model, arg, self.data_gen(arg))
+
+        return residual

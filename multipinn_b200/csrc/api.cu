@@ -1,0 +1,335 @@
+// api.cu -- the extern "C" boundary of libmpinn_b200.so (see include/mpinn_b200.h) plus the
+// small kernels around the jet engines: weight packing, sum-of-squares reduction, fused Adam.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace mpinn {
+
+static thread_local std::string g_err;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+static int fail_cuda(const char* what, cudaError_t e) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// tensor-core operand block of one square hidden layer, in floats (jet_tc.cu)
+int64_t tc_block_floats(int width);
+cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* packed,
+                           cudaStream_t stream);
+
+// Translate the host program into the device description: padded dims, packed-buffer offsets,
+// stash planes.  Returns an error string or nullptr.
+static const char* build_prog(const mpinn_op_t* ops, int n_ops, int d, int order, DevProg* out) {
+  if (!ops || n_ops <= 0) return "empty program";
+  if (n_ops > kMaxOps) return "program has more than MPINN_MAX_OPS ops";
+  if (d < 1 || d > 3) return "input dimension must be 1, 2 or 3";
+  if (order < 0 || order > 2) return "jet order must be 0, 1 or 2";
+  DevProg& p = *out;
+  memset(&p, 0, sizeof(p));
+  p.n_ops = n_ops;
+  p.d = d;
+  const int J = 1 + order * d;
+  int cur_w = d, max_w = round_up(d, 8), planes = 0;
+  int64_t pk = 0;
+  for (int l = 0; l < n_ops; ++l) {
+    const mpinn_op_t& s = ops[l];
+    DevOp& o = p.ops[l];
+    o.kind = s.kind;
+    o.in_dim = s.in_dim;
+    o.out_dim = s.out_dim;
+    o.act = s.act;
+    o.flags = s.flags;
+    o.w_off = s.w_off;
+    o.b_off = s.b_off;
+    o.stash_plane = -1;
+    o.tc_off = -1;
+    if (s.in_dim != cur_w) return "op in_dim does not match the previous op's out_dim";
+    if (s.in_dim < 1 || s.out_dim < 1) return "bad op dims";
+    if (s.kind == MPINN_OP_FOURIER) {
+      if (l != 0) return "FOURIER must be the first op";
+      if (s.out_dim % 2) return "FOURIER out_dim must be even";
+    } else if (s.kind == MPINN_OP_LINEAR) {
+      if (s.act < 0 || s.act > 2) return "bad activation";
+      if ((s.flags & MPINN_FLAG_ADD_SKIP) && s.out_dim != s.in_dim)
+        return "skip connection needs equal widths";
+      o.outp = round_up(s.out_dim, 8);
+      o.inp = round_up(s.in_dim, 8);
+      o.pk_fwd = (int)pk;
+      pk += (int64_t)s.in_dim * o.outp;
+      o.pk_bwd = (int)pk;
+      pk += (int64_t)s.out_dim * o.inp;
+      if (s.in_dim == s.out_dim && tc_block_floats(s.in_dim) > 0) {
+        pk = round_up64(pk, 256);  // 1 KiB alignment for UMMA operand tiles
+        o.tc_off = (int)pk;
+        pk += tc_block_floats(s.in_dim);
+      }
+      pk = round_up64(pk, 4);
+      const bool final_plain = (l == n_ops - 1) && s.act == MPINN_ACT_NONE;
+      if (!final_plain) {
+        o.stash_plane = planes;
+        planes += J * s.out_dim;
+      }
+      if (s.flags & (MPINN_FLAG_SAVE_SKIP | MPINN_FLAG_ADD_SKIP)) p.has_skip = 1;
+    } else {
+      return "unknown op kind";
+    }
+    cur_w = s.out_dim;
+    if (round_up(cur_w, 8) > max_w) max_w = round_up(cur_w, 8);
+  }
+  p.max_w = max_w;
+  p.n_out = cur_w;
+  p.total_planes = planes;
+  p.packed_floats = pk;
+  return nullptr;
+}
+
+struct DeviceInfo {
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  bool ok = false;
+};
+static cudaError_t device_info(DeviceInfo* info) {
+  static thread_local DeviceInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && cache[dev].ok) {
+    *info = cache[dev];
+    return cudaSuccess;
+  }
+  int v = 0;
+  e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  info->sm_count = v;
+  e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  info->smem_optin = (size_t)v;
+  info->ok = true;
+  if (dev >= 0 && dev < 64) cache[dev] = *info;
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------ kernels
+// forward operand Wt[k][f] = W[f][k] (zero padded to outp), reverse operand Wn[o][i] = W[o][i]
+// (zero padded to inp); tensor-core operand blocks are produced by launch_pack_tc (jet_tc.cu).
+
+__global__ void pack_params_kernel(const __grid_constant__ DevProg prog,
+                                   const float* __restrict__ params, float* __restrict__ packed) {
+  const DevOp& op = prog.ops[blockIdx.y];
+  if (op.kind != MPINN_OP_LINEAR) return;
+  const float* W = params + op.w_off;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  float* fw = packed + op.pk_fwd;
+  for (int i = tid; i < op.in_dim * op.outp; i += nth) {
+    const int k = i / op.outp, f = i % op.outp;
+    fw[i] = f < op.out_dim ? W[f * op.in_dim + k] : 0.0f;
+  }
+  float* bw = packed + op.pk_bwd;
+  for (int i = tid; i < op.out_dim * op.inp; i += nth) {
+    const int o = i / op.inp, k = i % op.inp;
+    bw[i] = k < op.in_dim ? W[o * op.in_dim + k] : 0.0f;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ r, int64_t n, int64_t stride,
+                             float* __restrict__ accum) {
+  float s = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = r[i * stride];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __shared__ float ws[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) ws[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < (int)(blockDim.x >> 5) ? ws[lane] : 0.0f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) atomicAdd(accum, s);
+  }
+}
+
+// torch.optim.Adam's single-tensor update, restated (see oracle/jet_ref.py:adam_step)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float one_minus_b1, float b2,
+                            float one_minus_b2, float step_size, float bc2_sqrt, float eps,
+                            float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = fmaf(one_minus_b1, gi - m[i], m[i]);
+  const float vi = fmaf(one_minus_b2 * gi, gi, v[i] * b2);
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - step_size * (mi / denom);
+}
+
+}  // namespace mpinn
+
+// ------------------------------------------------------------------------------------ C ABI
+using namespace mpinn;
+
+extern "C" {
+
+int mpinn_abi_version(void) { return MPINN_ABI_VERSION; }
+
+const char* mpinn_last_error(void) { return g_err.c_str(); }
+
+size_t mpinn_stash_bytes(const mpinn_op_t* ops, int n_ops, int d, int order, int64_t n_points) {
+  DevProg prog;
+  if (build_prog(ops, n_ops, d, order, &prog)) return 0;
+  return (size_t)prog.total_planes * (size_t)round_up64(n_points, 128) * sizeof(float);
+}
+
+// one private slab of n_params floats per resident CTA (at most 4 per SM on a 148-SM part)
+static const int kMaxSlabs = 148 * 4;
+
+size_t mpinn_backward_workspace_bytes(const mpinn_op_t* ops, int n_ops, int64_t n_params) {
+  (void)ops;
+  (void)n_ops;
+  return (size_t)kMaxSlabs * (size_t)n_params * sizeof(float);
+}
+
+size_t mpinn_packed_bytes(const mpinn_op_t* ops, int n_ops) {
+  DevProg prog;
+  if (build_prog(ops, n_ops, ops ? ops[0].in_dim : 0, 0, &prog)) return 0;
+  return (size_t)(prog.packed_floats + 256) * sizeof(float);
+}
+
+int mpinn_pack_params(const mpinn_op_t* ops, int n_ops, const float* params, void* packed,
+                      void* stream) {
+  DevProg prog;
+  const char* err = build_prog(ops, n_ops, ops ? ops[0].in_dim : 0, 0, &prog);
+  if (err) return fail(err);
+  if (!params || !packed) return fail("null pointer");
+  dim3 grid(16, n_ops);
+  pack_params_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prog, params, (float*)packed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda("pack_params", e);
+  e = launch_pack_tc(prog, params, (float*)packed, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("pack_params(tc)", e);
+  return 0;
+}
+
+static bool use_tc(const DevProg& prog, int d, int order, int engine, int* rc) {
+  *rc = 0;
+  if (engine == MPINN_ENGINE_FFMA) return false;
+  const bool ok = tc_supported(prog, d, order);
+  if (engine == MPINN_ENGINE_TCGEN05 && !ok) {
+    *rc = fail("tcgen05 engine requested but the program is not supported by it");
+    return false;
+  }
+  return ok;
+}
+
+int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, const void* packed,
+                      const float* x, int64_t n, int d, int order, float* out, void* stash,
+                      int engine, void* stream) {
+  DevProg prog;
+  const char* err = build_prog(ops, n_ops, d, order, &prog);
+  if (err) return fail(err);
+  if (ops[0].in_dim != d) return fail("first op in_dim must equal d");
+  if (n <= 0) return 0;
+  if (!params || !packed || !x || !out) return fail("null pointer");
+  DeviceInfo info;
+  cudaError_t e = device_info(&info);
+  if (e != cudaSuccess) return fail_cuda("device query", e);
+  const int64_t n_pad = round_up64(n, 128);
+  int rc;
+  if (use_tc(prog, d, order, engine, &rc)) {
+    e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
+                      info.sm_count, (cudaStream_t)stream);
+  } else {
+    if (rc) return rc;
+    e = launch_fwd_ffma(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash,
+                        n_pad, info.sm_count, info.smem_optin, (cudaStream_t)stream);
+  }
+  if (e == cudaErrorInvalidConfiguration)
+    return fail("layer widths too large for the shared-memory budget of this engine");
+  if (e != cudaSuccess) return fail_cuda("jet_forward", e);
+  return 0;
+}
+
+int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, const void* packed,
+                       const float* x, int64_t n, int d, int order, const float* dout,
+                       const void* stash, float* dparams, int64_t n_params, float* dx,
+                       void* workspace, size_t workspace_bytes, int engine, void* stream) {
+  DevProg prog;
+  const char* err = build_prog(ops, n_ops, d, order, &prog);
+  if (err) return fail(err);
+  if (n <= 0) return 0;
+  if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
+  if (dx) return fail("gradient w.r.t. the points (dx) is not implemented");
+  int slabs = (int)(workspace_bytes / ((size_t)n_params * sizeof(float)));
+  if (slabs < 1) return fail("backward workspace too small");
+  if (slabs > kMaxSlabs) slabs = kMaxSlabs;
+  DeviceInfo info;
+  cudaError_t e = device_info(&info);
+  if (e != cudaSuccess) return fail_cuda("device query", e);
+  const int64_t n_pad = round_up64(n, 128);
+  int rc;
+  if (use_tc(prog, d, order, engine, &rc)) {
+    e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
+                      n_pad, (float*)workspace, slabs, n_params, dparams, dx, info.sm_count,
+                      (cudaStream_t)stream);
+  } else {
+    if (rc) return rc;
+    e = launch_bwd_ffma(prog, params, (const float*)packed, x, n, d, order, dout,
+                        (const float*)stash, n_pad, (float*)workspace, slabs, n_params, dparams, dx,
+                        info.sm_count, info.smem_optin, (cudaStream_t)stream);
+  }
+  if (e == cudaErrorInvalidConfiguration)
+    return fail("layer widths too large for the shared-memory budget of this engine");
+  if (e != cudaSuccess) return fail_cuda("jet_backward", e);
+  return 0;
+}
+
+int mpinn_sumsq(const float* r, int64_t n, int64_t stride, float* accum, void* stream) {
+  if (n <= 0) return 0;
+  if (!r || !accum) return fail("null pointer");
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(r, n, stride, accum);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda("sumsq", e);
+  return 0;
+}
+
+int mpinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                    void* stream) {
+  if (n <= 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null pointer");
+  if (step < 1) return fail("step must be >= 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, 1.0f - beta1, beta2, 1.0f - beta2, step_size,
+      bc2_sqrt, eps, grad_scale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda("adam_step", e);
+  return 0;
+}
+
+}  // extern "C"

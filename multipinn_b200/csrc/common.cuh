@@ -1,0 +1,135 @@
+// common.cuh -- device-side program description and activation-jet algebra shared by all kernels.
+//
+// Jet algebra (restated from the reference's autograd behaviour, see oracle/jet_ref.py and
+// SURVEY.md section 8 a-J): per point and feature carry z (value), z_i = dz/dx_i, z_ii = d2z/dx_i2.
+//   a    = s0(z)
+//   a_i  = s1(z) z_i
+//   a_ii = s2(z) z_i^2 + s1(z) z_ii
+// with s_k the k-th derivative of the activation.  GELU is the reference's literal
+// x*0.5*(1+erf(x/1.41421)) (multipinn/neural_network/activation_function.py:14), Sine is sin x (:26).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpinn_b200.h"
+
+namespace mpinn {
+
+constexpr int kMaxOps = MPINN_MAX_OPS;
+
+struct DevOp {
+  int kind, in_dim, out_dim, act, flags;
+  int w_off, b_off;      // float offsets into the flat parameter vector
+  int pk_fwd, pk_bwd;    // float offsets into the packed buffer: Wt[in][outp] and Wn[out][inp]
+  int outp, inp;         // dims padded to a multiple of 8
+  int stash_plane;       // first stash plane (J*out_dim planes follow), -1 = not stashed
+  int tc_off;            // float offset of the tensor-core operand block in the packed buffer, -1 = none
+  int pad_;
+};
+
+struct DevProg {
+  int n_ops, max_w, has_skip, d, n_out, total_planes;
+  int64_t packed_floats;
+  DevOp ops[kMaxOps];
+};
+
+constexpr float kGeluC = 1.0f / 1.41421f;             // the reference's literal constant
+constexpr float kGeluC2 = kGeluC * kGeluC;
+constexpr float kInvSqrtPi = 0.5641895835477563f;
+
+// s0..s3 of the activation at z.  NEED3 selects whether the third derivative is produced.
+template <bool NEED3>
+__device__ __forceinline__ void act_coeffs(int act, float z, float& s0, float& s1, float& s2,
+                                           float& s3) {
+  if (act == MPINN_ACT_GELU) {
+    const float cz = kGeluC * z;
+    const float cz2 = cz * cz;
+    const float Phi = 0.5f * (1.0f + erff(cz));
+    const float phi = (kGeluC * kInvSqrtPi) * expf(-cz2);
+    s0 = z * Phi;
+    s1 = fmaf(z, phi, Phi);
+    s2 = phi * (2.0f - 2.0f * cz2);
+    s3 = NEED3 ? (-2.0f * kGeluC2) * z * phi * (4.0f - 2.0f * cz2) : 0.0f;
+  } else if (act == MPINN_ACT_SINE) {
+    float s, c;
+    sincosf(z, &s, &c);
+    s0 = s;
+    s1 = c;
+    s2 = -s;
+    s3 = -c;
+  } else {
+    s0 = z;
+    s1 = 1.0f;
+    s2 = 0.0f;
+    s3 = 0.0f;
+  }
+}
+
+// forward activation jets, in place: z[J] -> a[J]
+template <int D, int ORDER>
+__device__ __forceinline__ void act_jets(int act, float* z) {
+  if (act == MPINN_ACT_NONE) return;
+  float s0, s1, s2, s3;
+  act_coeffs<false>(act, z[0], s0, s1, s2, s3);
+  z[0] = s0;
+  if (ORDER >= 2) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[1 + D + i] = fmaf(s2 * z[1 + i], z[1 + i], s1 * z[1 + D + i]);
+  }
+  if (ORDER >= 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[1 + i] *= s1;
+  }
+}
+
+// cosine jets (Fourier encoding second half): z[J] -> cos jets
+template <int D, int ORDER>
+__device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj) {
+  float s, c;
+  sincosf(z[0], &s, &c);
+  sj[0] = s;
+  cj[0] = c;
+  if (ORDER >= 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      sj[1 + i] = c * z[1 + i];
+      cj[1 + i] = -s * z[1 + i];
+    }
+  }
+  if (ORDER >= 2) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const float zi2 = z[1 + i] * z[1 + i];
+      sj[1 + D + i] = fmaf(-s, zi2, c * z[1 + D + i]);
+      cj[1 + D + i] = fmaf(-c, zi2, -s * z[1 + D + i]);
+    }
+  }
+}
+
+// reverse of act_jets: given z[J] (pre-activation jets) and ab[J] (grad wrt activation jets),
+// overwrite ab with the grad wrt z.
+template <int D, int ORDER>
+__device__ __forceinline__ void act_jets_bwd(int act, const float* z, float* ab) {
+  if (act == MPINN_ACT_NONE) return;
+  float s0, s1, s2, s3;
+  act_coeffs<(ORDER >= 2)>(act, z[0], s0, s1, s2, s3);
+  float zb0 = ab[0] * s1;
+  if (ORDER >= 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const float zi = z[1 + i];
+      float zbi = ab[1 + i] * s1;
+      zb0 = fmaf(ab[1 + i] * s2, zi, zb0);
+      if (ORDER >= 2) {
+        const float aii = ab[1 + D + i];
+        zbi = fmaf(2.0f * aii * s2, zi, zbi);
+        zb0 = fmaf(aii, fmaf(s3 * zi, zi, s2 * z[1 + D + i]), zb0);
+        ab[1 + D + i] = aii * s1;
+      }
+      ab[1 + i] = zbi;
+    }
+  }
+  ab[0] = zb0;
+}
+
+}  // namespace mpinn

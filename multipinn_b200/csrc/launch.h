@@ -1,0 +1,31 @@
+// launch.h -- internal declarations shared by the translation units of libmpinn_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace mpinn {
+
+// FP32-FMA engine (jet_ffma.cu)
+cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const float* packed,
+                            const float* x, int64_t n, int d, int order, float* out, float* stash,
+                            int64_t n_pad, int sm_count, size_t smem_limit, cudaStream_t stream);
+cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const float* packed,
+                            const float* x, int64_t n, int d, int order, const float* dout,
+                            const float* stash, int64_t n_pad, float* part, int max_slabs,
+                            int64_t n_params, float* dparams, float* dx, int sm_count,
+                            size_t smem_limit, cudaStream_t stream);
+
+// tcgen05 engine (jet_tc.cu)
+bool tc_supported(const DevProg& prog, int d, int order);
+cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float* packed,
+                          const float* x, int64_t n, int d, int order, float* out, float* stash,
+                          int64_t n_pad, int sm_count, cudaStream_t stream);
+cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float* packed,
+                          const float* x, int64_t n, int d, int order, const float* dout,
+                          const float* stash, int64_t n_pad, float* part, int max_slabs,
+                          int64_t n_params, float* dparams, float* dx, int sm_count,
+                          cudaStream_t stream);
+
+}  // namespace mpinn

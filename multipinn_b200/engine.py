@@ -1,0 +1,241 @@
+"""Host side of the jet engine: the CUDA backend (ctypes -> libmpinn_b200.so) and the per-model
+``JetEngine`` that owns the flat parameter / gradient buffers and the packed kernel operands.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every number on the
+hot path is produced by the kernels in ``multipinn_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_backend = None
+
+
+class CudaBackend:
+    """Thin typed wrapper over the C ABI.  All tensors must be CUDA fp32 and contiguous."""
+
+    name = "cuda"
+    gpu_launches = 0  # kernels launched through this backend (reported by bench.py)
+
+    def __init__(self):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("multipinn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _ops(ops: np.ndarray):
+        return ops.ctypes.data_as(ctypes.c_void_p), int(ops.shape[0])
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        if t is None:
+            return ctypes.c_void_p(0)
+        assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+        return ctypes.c_void_p(t.data_ptr())
+
+    def stash_bytes(self, ops, d, order, n):
+        p, k = self._ops(ops)
+        return int(self.lib.mpinn_stash_bytes(p, k, d, order, n))
+
+    def workspace_bytes(self, ops, n_params):
+        p, k = self._ops(ops)
+        return int(self.lib.mpinn_backward_workspace_bytes(p, k, n_params))
+
+    def packed_bytes(self, ops):
+        p, k = self._ops(ops)
+        return int(self.lib.mpinn_packed_bytes(p, k))
+
+    def pack_params(self, ops, params, packed):
+        p, k = self._ops(ops)
+        _lib.check(self.lib.mpinn_pack_params(p, k, self._ptr(params), self._ptr(packed), self._stream()),
+                   "mpinn_pack_params")
+        CudaBackend.gpu_launches += 1
+
+    def jet_forward(self, ops, params, packed, x, order, out, stash, engine=_lib.ENGINE_AUTO):
+        p, k = self._ops(ops)
+        n, d = x.shape
+        _lib.check(self.lib.mpinn_jet_forward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
+                                              n, d, order, self._ptr(out), self._ptr(stash), engine,
+                                              self._stream()), "mpinn_jet_forward")
+        CudaBackend.gpu_launches += 1
+
+    def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace,
+                     engine=_lib.ENGINE_AUTO):
+        p, k = self._ops(ops)
+        n, d = x.shape
+        _lib.check(self.lib.mpinn_jet_backward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
+                                               n, d, order, self._ptr(dout), self._ptr(stash),
+                                               self._ptr(dparams), dparams.numel(), None,
+                                               self._ptr(workspace),
+                                               workspace.numel() * workspace.element_size(), engine,
+                                               self._stream()), "mpinn_jet_backward")
+        CudaBackend.gpu_launches += 2
+
+    def sumsq(self, r, accum):
+        """accum (0-d / 1-elem fp32) += sum(r**2); r is a 1-D fp32 view with any stride."""
+        assert r.dim() == 1 and r.is_cuda and r.dtype == torch.float32
+        _lib.check(self.lib.mpinn_sumsq(ctypes.c_void_p(r.data_ptr()), r.shape[0],
+                                        r.stride(0) if r.shape[0] > 1 else 1,
+                                        ctypes.c_void_p(accum.data_ptr()), self._stream()), "mpinn_sumsq")
+        CudaBackend.gpu_launches += 1
+
+    def adam_step(self, p, g, m, v, step, lr, beta1, beta2, eps, grad_scale=1.0):
+        _lib.check(self.lib.mpinn_adam_step(self._ptr(p), self._ptr(g), self._ptr(m), self._ptr(v),
+                                            p.numel(), int(step), float(lr), float(beta1), float(beta2),
+                                            float(eps), float(grad_scale), self._stream()),
+                   "mpinn_adam_step")
+        CudaBackend.gpu_launches += 1
+
+
+def backend():
+    """The process-wide backend.  Created on first use; raises if the CUDA path is unavailable."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def _set_backend_for_tests(b):
+    """Test hook: swap the kernel backend (used by the CPU test-suite to exercise host logic with
+    the oracle standing in for the GPU).  Never called by product code."""
+    global _backend
+    old = _backend
+    _backend = b
+    return old
+
+
+class JetEngine:
+    """Per-model state: layer program, flat parameter/gradient buffers (the module's parameters are
+    re-seated as views of them, so ``state_dict``/pickling/optimizers keep working), packed
+    operands, and the forward/backward entry points."""
+
+    COMM_TAIL = 128
+
+    def __init__(self, model: torch.nn.Module, program: np.ndarray):
+        self.model = model
+        self.ops = _lib.ops_array(program)
+        self.d = int(self.ops[0, 1])
+        self.n_out = int(self.ops[-1, 2])
+        self.kernel_engine = _lib.ENGINE_AUTO
+        self.flat: Optional[torch.Tensor] = None
+        self.flat_grad: Optional[torch.Tensor] = None
+        self.packed: Optional[torch.Tensor] = None
+        self.workspace: Optional[torch.Tensor] = None
+        self.packed_valid = False
+        self.managed = False  # a trainer promises to call invalidate() after each parameter update
+        self._params = []
+        self._offsets = []
+
+    # ---------------------------------------------------------------- flat buffers
+    def _is_flat(self) -> bool:
+        if self.flat is None:
+            return False
+        base = self.flat.data_ptr()
+        esz = self.flat.element_size()
+        params = list(self.model.parameters())
+        if len(params) != len(self._params):
+            return False
+        for p, off in zip(params, self._offsets):
+            if p.data_ptr() != base + off * esz or p.dtype != torch.float32:
+                return False
+        return True
+
+    def ensure_flat(self):
+        """(Re)build the flat buffers if the module's parameters moved (``.to(device)``, reload...)."""
+        if self._is_flat():
+            return
+        params = list(self.model.parameters())
+        if not params:
+            raise RuntimeError("model has no parameters")
+        dev = params[0].device
+        for p in params:
+            if p.dtype != torch.float32:
+                raise TypeError("multipinn_b200 runs fp32 parameters only (the reference parity contract)")
+            if p.device != dev:
+                raise RuntimeError("all parameters must live on one device")
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        # the gradient buffer has a tail so the data-parallel sync can append the loss scalars and
+        # send gradient + metrics as one message
+        self._grad_storage = torch.zeros(total + self.COMM_TAIL, dtype=torch.float32, device=dev)
+        grad = self._grad_storage[:total]
+        offs, off = [], 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            offs.append(off)
+            off += n
+        flat.requires_grad_(any(p.requires_grad for p in params))
+        flat.grad = grad if flat.requires_grad else None
+        self.flat, self.flat_grad = flat, grad
+        self._params, self._offsets = params, offs
+        self.attach_grads()
+        b = backend()
+        self.packed = torch.empty(max(b.packed_bytes(self.ops), 4) // 4 + 64, dtype=torch.float32, device=dev)
+        self.workspace = None
+        self.packed_valid = False
+
+    def comm_buffer(self, extra: int) -> torch.Tensor:
+        """``[P + extra]`` view: the flat gradient followed by ``extra`` scratch floats."""
+        if extra > self.COMM_TAIL:
+            raise ValueError(f"at most {self.COMM_TAIL} loss components fit the comm tail")
+        return self._grad_storage[: self.flat_grad.numel() + extra]
+
+    def attach_grads(self):
+        """Point every trainable parameter's ``.grad`` at its slice of the flat gradient buffer."""
+        for p, off in zip(self._params, self._offsets):
+            if p.requires_grad:
+                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.ensure_flat()
+        self.flat_grad.zero_()
+        if self.flat.requires_grad:
+            self.flat.grad = self.flat_grad
+        self.attach_grads()
+
+    def invalidate(self):
+        self.packed_valid = False
+
+    def _ensure_packed(self):
+        if not (self.packed_valid and self.managed):
+            backend().pack_params(self.ops, self.flat.detach(), self.packed)
+            self.packed_valid = True
+
+    # ---------------------------------------------------------------- kernels
+    def forward(self, x: torch.Tensor, order: int, need_stash: bool):
+        """x [N,d] fp32 contiguous -> (out [J,N,o], stash or None)."""
+        self.ensure_flat()
+        self._ensure_packed()
+        b = backend()
+        n, d = x.shape
+        J = 1 + order * d
+        out = torch.empty((J, n, self.n_out), dtype=torch.float32, device=x.device)
+        stash = None
+        if need_stash:
+            nbytes = b.stash_bytes(self.ops, d, order, n)
+            stash = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=x.device)
+        b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine)
+        return out, stash
+
+    def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor):
+        """Returns the flat parameter gradient [P] for dL/d(out jets) = dout."""
+        b = backend()
+        if self.workspace is None or self.workspace.device != x.device:
+            nbytes = b.workspace_bytes(self.ops, self.flat.numel())
+            self.workspace = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+        dflat = torch.zeros_like(self.flat_grad)
+        b.jet_backward(self.ops, self.flat.detach(), self.packed, x, order, dout, stash, dflat,
+                       self.workspace, self.kernel_engine)
+        return dflat

@@ -1,0 +1,23 @@
+"""Minimal axis-aligned box geometry: just enough of the reference's ``Hypercube``
+(reference ``multipinn/geometry/domain_nd.py:12-126``) to feed conditions with collocation points
+(``bbox``, ``random_points``).  Geometry/CSG is outside the accelerated path."""
+import numpy as np
+
+
+class Hypercube:
+    def __init__(self, low, high):
+        if len(low) != len(high):
+            raise ValueError("Dimensions of low and high do not match.")
+        self.low = np.array(low, dtype="float32")
+        self.high = np.array(high, dtype="float32")
+        if np.any(self.low > self.high):
+            raise ValueError("low > high")
+        self.dim = len(low)
+        self.bbox = (self.low, self.high)
+        self.side_length = self.high - self.low
+
+    def random_points(self, n, random="pseudo"):
+        if random != "pseudo":
+            raise NotImplementedError("only the pseudo-random sampler is provided here")
+        x = np.random.random(size=(n, self.dim)).astype("float32")
+        return self.side_length * x + self.low

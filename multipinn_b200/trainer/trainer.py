@@ -1,0 +1,286 @@
+"""Training loop with the reference's interface (reference ``multipinn/trainer/trainer.py:9-338``):
+``Trainer`` (gradient accumulation over ``num_batches``), ``TrainerOneBatch`` and the data-parallel
+``TrainerMultiGPU``.
+
+What is different underneath:
+  * the gradient lives in ONE flat buffer (the model's parameters and ``.grad`` are views of flat
+    storage owned by the ``JetEngine``), so ``zero_grad`` is one memset and the data-parallel sync
+    is ONE all-reduce of ``[P + K + 1]`` floats (gradient, K component losses, total loss) instead of
+    one call per parameter tensor plus two for the metrics (reference trainer.py:242-258);
+  * ``optimizer.step()`` for a plain ``torch.optim.Adam`` runs as one fused kernel over the flat
+    buffers; its moments are exposed through ``optimizer.state`` so checkpoints keep working.
+    Any other optimizer is stepped through its own ``step()``;
+  * rank 0's parameters are broadcast once at start (the reference never synchronises replicas).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Union
+
+import torch
+import torch.distributed as dist
+
+from .. import jet
+from ..engine import backend
+from ..neural_network.base import JetModule
+from ..PINN import PINN
+
+
+class _FlatAdam:
+    """Fused Adam over the engine's flat buffers, mirrored into ``optimizer.state``."""
+
+    def __init__(self, engine, optimizer: torch.optim.Adam):
+        self.engine = engine
+        self.optimizer = optimizer
+        engine.ensure_flat()
+        self.m = torch.zeros_like(engine.flat_grad)
+        self.v = torch.zeros_like(engine.flat_grad)
+        self.step = 0
+        for p, off in zip(engine._params, engine._offsets):
+            st = optimizer.state.get(p)
+            if st:  # resume from an existing torch state
+                self.m[off:off + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                self.v[off:off + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step = max(self.step, int(st["step"]))
+        self._publish()
+
+    @staticmethod
+    def eligible(engine, optimizer) -> bool:
+        if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        if g.get("amsgrad") or g.get("weight_decay", 0) != 0 or g.get("maximize") or \
+                g.get("capturable") or g.get("differentiable"):
+            return False
+        engine.ensure_flat()
+        return {id(p) for p in g["params"]} == {id(p) for p in engine._params}
+
+    def _publish(self):
+        for p, off in zip(self.engine._params, self.engine._offsets):
+            if not p.requires_grad:
+                continue
+            n = p.numel()
+            self.optimizer.state[p] = {
+                "step": torch.tensor(float(self.step)),
+                "exp_avg": self.m[off:off + n].view(p.shape),
+                "exp_avg_sq": self.v[off:off + n].view(p.shape),
+            }
+
+    def apply(self, grad_scale: float = 1.0):
+        g = self.optimizer.param_groups[0]
+        self.step += 1
+        b1, b2 = g["betas"]
+        backend().adam_step(self.engine.flat.detach(), self.engine.flat_grad, self.m, self.v, self.step,
+                            g["lr"], b1, b2, g["eps"], grad_scale)
+        for p in self.engine._params:
+            st = self.optimizer.state.get(p)
+            if st is not None:
+                st["step"].fill_(float(self.step))
+        self.optimizer._opt_called = True  # what LRScheduler checks before its first step()
+
+
+class Trainer:
+    def __init__(
+        self,
+        pinn: PINN,
+        optimizer: torch.optim.Optimizer,
+        scheduler: torch.optim.lr_scheduler.LRScheduler,
+        num_epochs: int = 1000,
+        num_batches: int = 1,
+        update_grid_every: int = 1,
+        calc_loss: Union[str, Callable[[], List[torch.Tensor]]] = "mean",
+        callbacks_organizer=None,
+        mixed_training: bool = False,
+    ) -> None:
+        self.pinn = pinn
+        self.optimizer = optimizer
+        self.scheduler = scheduler
+        self.num_epochs = num_epochs
+        self.num_batches = num_batches
+        self.update_grid_every = update_grid_every if update_grid_every is not None else num_epochs + 1
+        if isinstance(calc_loss, str):
+            if calc_loss == "mean":
+                self.calc_loss = self.mean_calc_loss
+            elif calc_loss == "legacy":
+                self.calc_loss = self.sum_of_means_calc_loss
+            else:
+                raise ValueError
+        else:
+            self.calc_loss = calc_loss
+        self.callbacks_organizer = callbacks_organizer
+        if mixed_training:
+            raise NotImplementedError(
+                "mixed_training (fp16 autocast) is not part of the fused fp32-class path")
+        self.mixed_training = False
+        self.current_epoch = 0
+        self.current_batch = 0
+        self.inum_batches = 1.0 / self.num_batches
+        self.epoch_loss_detailed = None
+        self.total_loss = None
+        self.current_lr = None
+        for cond in self.pinn.conditions:
+            cond.set_batching(self.num_batches)
+        model = self.pinn.model
+        self._engine = model.jet_engine if isinstance(model, JetModule) else None
+        self._flat_adam = None
+        if self._engine is not None:
+            self._engine.ensure_flat()
+            self._engine.managed = True
+            self._engine.invalidate()
+            if _FlatAdam.eligible(self._engine, optimizer):
+                self._flat_adam = _FlatAdam(self._engine, optimizer)
+
+    # ---------------------------------------------------------------- loop (reference :74-117)
+    def train(self):
+        for self.current_epoch in range(self.num_epochs + 1):
+            self._train_epoch()
+            if self.scheduler is not None:
+                self.scheduler.step()
+                self.current_lr = self.optimizer.param_groups[0]["lr"]
+            self._run_callbacks()
+
+    def _run_callbacks(self):
+        if self.callbacks_organizer is None:
+            return
+        self.pinn.model.eval()
+        with torch.no_grad():
+            for callback in self.callbacks_organizer.base_callbacks:
+                callback(self)
+        self.pinn.model.train()
+        for callback in self.callbacks_organizer.grad_callbacks:
+            callback(self)
+
+    def _train_epoch(self):
+        self.pinn.model.train()
+        if self.current_epoch % self.update_grid_every == 0:
+            self.pinn.update_data()
+        self.epoch_loss_detailed = None
+        self.total_loss = 0
+        jet.clear_blocks()
+        self._train_batches()
+
+    def _accumulate(self, batch_loss, losses):
+        d = losses.detach()
+        self.epoch_loss_detailed = d if self.epoch_loss_detailed is None else self.epoch_loss_detailed + d
+        self.total_loss = self.total_loss + batch_loss.detach()
+
+    def _zero_grad(self):
+        if self._engine is not None:
+            self._engine.zero_grad()
+        else:
+            self.optimizer.zero_grad()
+
+    def _optimizer_step(self, grad_scale: float = 1.0):
+        if self._flat_adam is not None:
+            self._flat_adam.apply(grad_scale)
+        else:
+            if grad_scale != 1.0:
+                for p in self.pinn.model.parameters():
+                    if p.grad is not None:
+                        p.grad.mul_(grad_scale)
+            self.optimizer.step()
+        if self._engine is not None:
+            self._engine.invalidate()
+
+    def _train_batches(self):
+        self._zero_grad()  # outside the loop: gradients accumulate over the batches
+        for self.current_batch in range(self.num_batches):
+            self.pinn.select_batch(self.current_batch)
+            batch_loss, losses = self.calc_loss(self)
+            batch_loss.backward()
+            self._accumulate(batch_loss, losses)
+        self._optimizer_step()
+        self.epoch_loss_detailed = self.epoch_loss_detailed * self.inum_batches
+        self.total_loss = self.total_loss * self.inum_batches
+
+    # ---------------------------------------------------------------- loss policies (:155-180)
+    @staticmethod
+    def sum_of_means_calc_loss(self: "Trainer"):
+        losses = torch.stack(self.pinn.calculate_loss())
+        return torch.sum(losses), losses
+
+    @staticmethod
+    def mean_calc_loss(self: "Trainer"):
+        total_loss, losses_list = self.pinn.calculate_mean_loss()
+        return total_loss, torch.stack(losses_list)
+
+
+class TrainerOneBatch(Trainer):
+    def __init__(self, pinn, optimizer, scheduler, num_epochs: int = 1000, update_grid_every: int = 1,
+                 calc_loss="mean", callbacks_organizer=None, mixed_training: bool = False) -> None:
+        super().__init__(pinn, optimizer, scheduler, num_epochs, 1, update_grid_every, calc_loss,
+                         callbacks_organizer, mixed_training)
+
+    def _train_batches(self):
+        self.pinn.select_batch(0)
+        self._zero_grad()
+        batch_loss, losses = self.calc_loss(self)
+        batch_loss.backward()
+        self._optimizer_step()
+        self._accumulate(batch_loss, losses)
+
+
+class TrainerMultiGPU(Trainer):
+    """One process per GPU; rank r trains on slice r of every condition's points
+    (reference trainer.py:183-284) and the replicas exchange one flat message per step."""
+
+    def __init__(self, pinn, optimizer, scheduler, num_epochs: int = 1000, num_batches: int = 1,
+                 update_grid_every: int = 1, calc_loss="mean", callbacks_organizer=None,
+                 mixed_training: bool = False, rank: int = 0) -> None:
+        super().__init__(pinn, optimizer, scheduler, num_epochs, num_batches, update_grid_every,
+                         calc_loss, callbacks_organizer, mixed_training)
+        self.rank = rank
+        assert dist.get_world_size() == num_batches
+        self._comm = None
+        if self._engine is not None:  # replicas must start from identical weights
+            dist.broadcast(self._engine.flat.detach(), src=0)
+            self._engine.invalidate()
+        else:
+            for p in self.pinn.model.parameters():
+                dist.broadcast(p.data, src=0)
+
+    def _train_batches(self):
+        self._zero_grad()
+        self.pinn.select_batch(self.rank)
+        batch_loss, losses = self.calc_loss(self)
+        batch_loss.backward()
+        self._accumulate(batch_loss, losses)
+        self.reduce_gradients()
+        self._optimizer_step()
+        self.reduce_metrics()
+
+    def reduce_gradients(self):
+        """After this call every ``p.grad`` is the mean over ranks (reference :242-251) -- done with one
+        all-reduce that also carries the logged losses."""
+        world = float(dist.get_world_size())
+        if self._engine is None:
+            for p in self.pinn.model.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad.data, op=dist.ReduceOp.SUM)
+                    p.grad.data /= world
+            self._comm = None
+            return
+        eng = self._engine
+        P = eng.flat_grad.numel()
+        K = self.epoch_loss_detailed.numel()
+        msg = eng.comm_buffer(K + 1)
+        msg[P:P + K].copy_(self.epoch_loss_detailed.reshape(-1))
+        msg[P + K:P + K + 1].copy_(self.total_loss.reshape(-1))
+        dist.all_reduce(msg, op=dist.ReduceOp.SUM)
+        msg.mul_(1.0 / world)
+        self._comm = (msg, P, K)
+
+    def reduce_metrics(self):
+        """``total_loss`` / ``epoch_loss_detailed`` become means over ranks (reference :253-258)."""
+        if self._comm is not None:
+            msg, P, K = self._comm
+            self.epoch_loss_detailed = msg[P:P + K].clone().reshape(self.epoch_loss_detailed.shape)
+            self.total_loss = msg[P + K].clone()
+            return
+        dist.all_reduce(self.total_loss, op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.epoch_loss_detailed, op=dist.ReduceOp.SUM)
+        self.total_loss /= dist.get_world_size()
+        self.epoch_loss_detailed /= dist.get_world_size()
+
+    def _run_callbacks(self):
+        if self.rank == 0:
+            super()._run_callbacks()

@@ -1,0 +1,54 @@
+"""TEST-ONLY kernel backend: implements the ``multipinn_b200.engine`` backend interface with the
+numpy oracle (oracle/jet_ref.py) on CPU tensors, so the host-side logic (jet-block decoding,
+plans, flat buffers, trainers, gloo data-parallel) can be exercised without a GPU.  Product code
+never imports this."""
+import numpy as np
+import torch
+
+from oracle import jet_ref as JR
+
+
+class OracleBackend:
+    name = "oracle"
+
+    def __init__(self, dtype=np.float64):
+        self.dtype = dtype
+        self.calls = []
+
+    def stash_bytes(self, ops, d, order, n):
+        return 4
+
+    def workspace_bytes(self, ops, n_params):
+        return 4
+
+    def packed_bytes(self, ops):
+        return 4
+
+    def pack_params(self, ops, params, packed):
+        self.calls.append("pack")
+
+    def _np(self, t):
+        return t.detach().cpu().numpy().astype(self.dtype)
+
+    def jet_forward(self, ops, params, packed, x, order, out, stash, engine=0):
+        self.calls.append(("fwd", int(order), int(x.shape[0])))
+        o, _ = JR.forward(ops, self._np(params), self._np(x), order)
+        out.copy_(torch.from_numpy(np.ascontiguousarray(o.transpose(1, 0, 2))).to(out.dtype))
+
+    def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace, engine=0):
+        self.calls.append(("bwd", int(order), int(x.shape[0])))
+        p, xx = self._np(params), self._np(x)
+        _, cache = JR.forward(ops, p, xx, order)
+        dp, _ = JR.backward(ops, p, xx, order, cache, self._np(dout).transpose(1, 0, 2))
+        # frozen Fourier encodings get no gradient from the fused reverse pass
+        ops = np.asarray(ops).reshape(-1, 8)
+        if ops[0, 0] == JR.OP_FOURIER:
+            dp[ops[0, 3]: ops[0, 3] + ops[0, 1] * ops[0, 2] // 2] = 0
+        dparams.add_(torch.from_numpy(dp).to(dparams.dtype))
+
+    def sumsq(self, r, accum):
+        accum.add_(torch.sum(r.detach().double() ** 2).to(accum.dtype))
+
+    def adam_step(self, p, g, m, v, step, lr, beta1, beta2, eps, grad_scale=1.0):
+        self.calls.append(("adam", int(step)))
+        JR.adam_step(p.numpy(), g.numpy(), m.numpy(), v.numpy(), step, lr, beta1, beta2, eps, grad_scale)

@@ -1,0 +1,284 @@
+"""Host-side logic of the product (jet-block decoding, residual plans, flat buffers, PINN, trainers)
+exercised on CPU with the oracle standing in for the kernels (tests/oracle_backend.py), and checked
+against vectors from the unmodified reference (tests/golden)."""
+import copy
+import io
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import multipinn_b200 as mp
+from multipinn_b200 import engine, jet
+from oracle import autograd_ref as AR
+from tests import problems
+from tests.oracle_backend import OracleBackend
+from tests.test_oracle_golden import GOLD_KW, NAMES, load, relerr
+
+MODELS = {"FNN": mp.FNN, "ResNet": mp.ResNet, "FFNN": mp.FFNN}
+
+
+@pytest.fixture(autouse=True)
+def oracle_backend():
+    be = OracleBackend()
+    old = engine._set_backend_for_tests(be)
+    jet.clear_blocks()
+    yield be
+    engine._set_backend_for_tests(old)
+
+
+def product_ns():
+    return types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack, Symbols=mp.Symbols)
+
+
+def product_model(name, g):
+    _, kind, _ = problems.CONFIGS[name]
+    m = MODELS[kind](int(g["input_dim"]), int(g["output_dim"]), **GOLD_KW[name])
+    sd = {k: torch.tensor(g["w::" + k]) for k in g["state_keys"]}
+    m.load_state_dict(sd, strict=True)  # same state_dict keys as the reference classes
+    return m
+
+
+class _Gen:
+    def __init__(self, pts):
+        self.pts, self.n_points = pts, len(pts)
+
+    def generate(self, cond, model):
+        return self.pts
+
+
+def build_pinn(name, g, world=1):
+    model = product_model(name, g)
+    conds_spec, din, dout = problems.CONFIGS[name][0](product_ns())
+    conds = []
+    for i, (fn, (lo, hi)) in enumerate(conds_spec):
+        c = mp.Condition(fn, mp.Hypercube(lo, hi))
+        c.generator = _Gen(torch.tensor(g[f"pts{i}"]).requires_grad_())
+        conds.append(c)
+    pinn = mp.PINN(model, conds)
+    pinn.update_data()
+    for c in conds:
+        c.set_batching(world)
+    return model, conds, pinn
+
+
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", NAMES)
+def test_program_matches_oracle_lowering(name):
+    g = load(name)
+    m = product_model(name, g)
+    prog, flat = AR.build_program(m)
+    assert np.array_equal(m.jet_program(), prog)
+    assert flat.shape[0] == sum(p.numel() for p in m.parameters())
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_residuals_loss_and_gradient_match_reference(name, oracle_backend):
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    pinn.select_batch(0)
+    k = 0
+    for ci, c in enumerate(conds):
+        for r in c.get_residual(model):
+            assert relerr(r.detach().numpy(), g[f"res{ci}_{k}_f64"]) < 1e-5, (ci, k)
+            k += 1
+    model.jet_engine.zero_grad()
+    total, losses = pinn.calculate_mean_loss()
+    assert relerr(total.detach().numpy(), g["total_f64"]) < 1e-5
+    assert relerr(torch.stack(losses).detach().numpy(), g["losses_f64"]) < 1e-5
+    legacy = torch.sum(torch.stack(pinn.calculate_loss()))
+    assert relerr(legacy.detach().numpy(), g["legacy_f64"]) < 1e-5
+    total.backward()
+    flat_grad = model.jet_engine.flat_grad.numpy()
+    assert relerr(flat_grad, g["grad_f64"]) < 1e-5
+    # per-parameter .grad are views of the flat buffer
+    got = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                          for p in model.parameters()])
+    assert np.array_equal(got, flat_grad)
+
+
+def test_plan_discovers_orders_once(oracle_backend):
+    g = load("poisson_2D_1C")
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    assert conds[0].plan_for(model).orders == [2]          # inner: u_xx, u_yy
+    assert all(c.plan_for(model).orders == [0] for c in conds[1:])  # Dirichlet sides: values only
+    oracle_backend.calls.clear()
+    pinn.select_batch(0)
+    pinn.calculate_mean_loss()
+    fwd = [c for c in oracle_backend.calls if c[0] == "fwd"]
+    assert [c[1] for c in fwd] == [2, 0, 0, 0, 0]           # one launch per model call, no re-runs
+
+    g = load("allen_cahn_2D_1C")
+    model, conds, pinn = build_pinn("allen_cahn_2D_1C", g)
+    assert [c.plan_for(model).orders for c in conds] == [[2], [1], [1], [0]]
+    g = load("burgers_1D")
+    model, conds, pinn = build_pinn("burgers_1D", g)
+    assert [c.plan_for(model).orders for c in conds] == [[2], [0, 0], [0]]
+
+
+def test_grad_without_plan_escalates_lazily(oracle_backend):
+    g = load("poisson_2D_1C")
+    model = product_model("poisson_2D_1C", g)
+    fn = problems.poisson_2D_1C(product_ns())[0][0][0]
+    pts = torch.tensor(g["pts0"]).requires_grad_()
+    (r,) = fn(model, pts)  # bare call, no Condition: orders 0 -> 1 -> 2 on demand
+    assert relerr(r.detach().numpy(), g["res0_0_f64"]) < 1e-5
+    assert [c[1] for c in oracle_backend.calls if c[0] == "fwd"] == [0, 1, 2]
+    oracle_backend.calls.clear()
+    with mp.jet_order(2):
+        (r2,) = fn(model, pts)
+    assert [c[1] for c in oracle_backend.calls if c[0] == "fwd"] == [2]
+    assert torch.equal(r, r2)
+
+
+def test_indexing_style_access(oracle_backend):
+    """f[:, k] / grad(...)[:, i] indexing (reference examples/poisson_3D/problem.py:22-29) decodes too."""
+    g = load("navier_stokes_3D")
+    model = product_model("navier_stokes_3D", g)
+    pts = torch.tensor(g["pts0"]).requires_grad_()
+    with mp.jet_order(2):
+        f = model(pts)
+        gu = mp.grad(f[:, 1], pts)
+        v_yy = mp.grad(gu[:, 1], pts)[:, 1]
+    assert relerr(gu.detach().numpy(), g["du_f64"][:, 1, :]) < 1e-5
+    assert relerr(v_yy.detach().numpy(), g["d2u_f64"][:, 1, 1]) < 1e-5
+
+
+def test_unsupported_derivatives_raise(oracle_backend):
+    g = load("poisson_2D_1C")
+    model = product_model("poisson_2D_1C", g)
+    pts = torch.tensor(g["pts0"]).requires_grad_()
+    (u,) = mp.unpack(model(pts))
+    with pytest.raises(mp.UnsupportedDerivative):
+        mp.grad(u * 2.0, pts)                      # derived expression, not a model output view
+    with pytest.raises(mp.UnsupportedDerivative):
+        mp.grad(u, pts.clone())                    # not the tensor the model saw
+    u_x, u_y = mp.unpack(mp.grad(u, pts))
+    u_xx, u_xy = mp.unpack(mp.grad(u_x, pts))
+    assert bool(torch.isnan(u_xy).all())           # mixed partial is poisoned, never silently wrong
+    with pytest.raises(mp.UnsupportedDerivative):
+        mp.grad(u_xx, pts)                         # third order
+
+    def mixed(model, arg):
+        (u,) = mp.unpack(model(arg))
+        u_x, u_y = mp.unpack(mp.grad(u, arg))
+        u_xx, u_xy = mp.unpack(mp.grad(u_x, arg))
+        return [u_xy]
+
+    c = mp.Condition(mixed, mp.Hypercube([0, 0], [1, 1]))
+    with pytest.raises(mp.UnsupportedDerivative):
+        c.init_output_len(model)
+
+
+def test_symbols_generated_source():
+    s = mp.Symbols(variables="x, y", functions="u")
+    fn = s("u, u_x, u_yy")
+    assert "(u,) = unpack(model(arg))" in fn.source
+    assert "u_x, u_y = unpack(grad(u, arg))" in fn.source
+    assert "u_yx, u_yy = unpack(grad(u_y, arg))" in fn.source
+    assert fn.source.strip().endswith("return u, u_x, u_yy")
+    with pytest.raises(ValueError):
+        mp.Symbols("x, x", "u")
+    with pytest.raises(ValueError):
+        s("w_x")
+
+
+def test_condition_batching_slices():
+    """select_batch / set_batching (reference tests/condition/test_condition.py:59-81)."""
+    c = mp.Condition(lambda m, a: [a[:, 0]], mp.Hypercube([0, 0], [1, 1]))
+    c.generator = types.SimpleNamespace(n_points=100)
+    c.points = torch.arange(200.0).reshape(100, 2)
+    c.set_batching(4)
+    assert c.batch_size == 25
+    c.select_batch(2)
+    assert torch.equal(c.batch_points, c.points[50:75])
+    with pytest.raises(AssertionError):
+        c.set_batching(3)
+
+
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D", "navier_stokes_3D", "burgers_1D"])
+def test_trainer_steps_match_reference(name, oracle_backend):
+    """TrainerOneBatch + torch Adam (fused flat Adam underneath) follows the reference's 3-step
+    trajectory: loss per step and parameters after steps 1 and 3."""
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=3, update_grid_every=10**9, calc_loss="mean")
+    assert tr._flat_adam is not None
+    traj = []
+    for e in range(3):
+        tr.current_epoch = e + 1
+        tr._train_epoch()
+        sched.step()
+        traj.append(float(tr.total_loss))
+        if e == 0:
+            flat = model.jet_engine.flat.detach().numpy().copy()
+            # first Adam step moves every weight by ~lr*g/(|g|+eps): a weight whose gradient is of the
+            # order of eps amplifies fp32 round-off in g, hence 0.5% of lr rather than an ulp bound
+            assert np.abs(flat - g["params_after1"]).max() < 5e-6
+            assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_step1"]) < 1e-5
+    assert relerr(np.array(traj), g["traj_f32"]) < 2e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - g["params_after3"]).max() < 1e-5
+    p0 = [p for p in model.parameters() if p.requires_grad][0]
+    st = opt.state[p0]
+    assert float(st["step"]) == 3.0 and st["exp_avg"].shape == p0.shape
+
+
+def test_trainer_accumulates_batches(oracle_backend):
+    """num_batches=2 accumulation (reference trainer.py:130-153) == mean of the two half-batch grads."""
+    g = load("allen_cahn_2D_1C")
+    model, conds, pinn = build_pinn("allen_cahn_2D_1C", g)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)  # non-Adam optimizer -> generic step path
+    tr = mp.Trainer(pinn, opt, None, num_epochs=1, num_batches=2, update_grid_every=10**9)
+    assert tr._flat_adam is None
+    tr.current_epoch = 1
+    tr._train_epoch()
+    got = model.jet_engine.flat_grad.numpy().copy()
+    grads = []
+    for b in range(2):
+        model.jet_engine.zero_grad()
+        pinn.select_batch(b)
+        total, _ = pinn.calculate_mean_loss()
+        total.backward()
+        grads.append(model.jet_engine.flat_grad.numpy().copy())
+    assert relerr(got, grads[0] + grads[1]) < 1e-6
+
+
+def test_state_dict_pickle_and_move(oracle_backend):
+    g = load("navier_stokes_2D")
+    model = product_model("navier_stokes_2D", g)
+    pts = torch.tensor(g["pts0"])
+    with torch.no_grad():
+        y0 = model(pts).clone()
+    sd = copy.deepcopy(model.state_dict())
+    assert list(sd.keys()) == list(g["state_keys"])
+    buf = io.BytesIO()
+    torch.save(model, buf)  # what the reference's SaveModel callback does (callbacks/save.py:79)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    with torch.no_grad():
+        assert torch.equal(m2(pts), y0)
+    # in-place parameter edits through the nn.Parameter views are seen by the engine
+    with torch.no_grad():
+        next(iter(model.parameters())).mul_(0.5)
+        assert not torch.equal(model(pts), y0)
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        assert torch.equal(model(pts), y0)
+
+
+def test_inference_under_no_grad_skips_stash(oracle_backend):
+    g = load("poisson_2D_1C")
+    model = product_model("poisson_2D_1C", g)
+    pts = torch.tensor(g["pts0"])
+    with torch.no_grad():
+        y = model(pts)
+    assert not y.requires_grad
+    assert relerr(y.numpy(), g["u_f64"]) < 1e-5
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(4, 3))      # wrong input dim
+    with pytest.raises(TypeError):
+        model(pts.double())           # fp32 only

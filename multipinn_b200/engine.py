@@ -22,6 +22,20 @@ class CudaBackend:
 
     name = "cuda"
     gpu_launches = 0  # kernels launched through this backend (reported by bench.py)
+    timings = None    # bench.py sets this to a list to get (kind, n, order, start_evt, end_evt) per launch
+
+    def _timed(self, kind, n, order):
+        if CudaBackend.timings is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (kind, n, order, e0)
+
+    def _timed_end(self, tok):
+        if tok is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            CudaBackend.timings.append(tok + (e1,))
 
     def __init__(self):
         self.lib = _lib.load()
@@ -64,21 +78,25 @@ class CudaBackend:
     def jet_forward(self, ops, params, packed, x, order, out, stash, engine=_lib.ENGINE_AUTO):
         p, k = self._ops(ops)
         n, d = x.shape
+        tok = self._timed("fwd", n, order)
         _lib.check(self.lib.mpinn_jet_forward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
                                               n, d, order, self._ptr(out), self._ptr(stash), engine,
                                               self._stream()), "mpinn_jet_forward")
+        self._timed_end(tok)
         CudaBackend.gpu_launches += 1
 
     def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace,
                      engine=_lib.ENGINE_AUTO):
         p, k = self._ops(ops)
         n, d = x.shape
+        tok = self._timed("bwd", n, order)
         _lib.check(self.lib.mpinn_jet_backward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
                                                n, d, order, self._ptr(dout), self._ptr(stash),
                                                self._ptr(dparams), dparams.numel(), None,
                                                self._ptr(workspace),
                                                workspace.numel() * workspace.element_size(), engine,
                                                self._stream()), "mpinn_jet_backward")
+        self._timed_end(tok)
         CudaBackend.gpu_launches += 2
 
     def sumsq(self, r, accum):

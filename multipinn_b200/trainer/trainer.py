@@ -225,10 +225,13 @@ class TrainerMultiGPU(Trainer):
 
     def __init__(self, pinn, optimizer, scheduler, num_epochs: int = 1000, num_batches: int = 1,
                  update_grid_every: int = 1, calc_loss="mean", callbacks_organizer=None,
-                 mixed_training: bool = False, rank: int = 0) -> None:
+                 mixed_training: bool = False, rank: int = 0, sharded_points: bool = False) -> None:
         super().__init__(pinn, optimizer, scheduler, num_epochs, num_batches, update_grid_every,
                          calc_loss, callbacks_organizer, mixed_training)
         self.rank = rank
+        # sharded_points=True: every rank's conditions hold ONLY that rank's slice (generators report
+        # the global n_points); the reference instead generates all points on every rank and uses 1/N
+        self.sharded_points = sharded_points
         assert dist.get_world_size() == num_batches
         self._comm = None
         if self._engine is not None:  # replicas must start from identical weights
@@ -240,7 +243,7 @@ class TrainerMultiGPU(Trainer):
 
     def _train_batches(self):
         self._zero_grad()
-        self.pinn.select_batch(self.rank)
+        self.pinn.select_batch(0 if self.sharded_points else self.rank)
         batch_loss, losses = self.calc_loss(self)
         batch_loss.backward()
         self._accumulate(batch_loss, losses)

@@ -80,6 +80,12 @@ int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* param
                        float* dx, void* workspace, size_t workspace_bytes, int engine,
                        void* stream);
 
+/* Diagnostic: one 128x64x64 (mode 0, K-major operands: c = a[128][64] * b[64][64]^T) or 128x64x128
+ * (mode 1, MN-major operands: c[128][64] = [hi(a)|lo(a)]^T * b with a,b [128][64]; rows 0..63 plus
+ * rows 64..127 give a^T b) 3xTF32 tcgen05.mma product through the same descriptor/layout helpers the
+ * jet kernels use.  Exists so the tensor-core conventions can be pinned in isolation by tests. */
+int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream);
+
 /* sum_i r[i*stride]^2 added into *accum (device scalar).
  * Replaces `torch.sum(r**2)` (reference PINN/PINN.py:59,95,123). */
 int mpinn_sumsq(const float* r, int64_t n, int64_t stride, float* accum, void* stream);

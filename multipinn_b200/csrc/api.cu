@@ -230,10 +230,10 @@ int mpinn_pack_params(const mpinn_op_t* ops, int n_ops, const float* params, voi
   return 0;
 }
 
-static bool use_tc(const DevProg& prog, int d, int order, int engine, int* rc) {
+static bool use_tc(const DevProg& prog, int d, int order, int engine, bool backward, int* rc) {
   *rc = 0;
   if (engine == MPINN_ENGINE_FFMA) return false;
-  const bool ok = tc_supported(prog, d, order);
+  const bool ok = backward ? tc_backward_supported(prog, d, order) : tc_forward_supported(prog, d, order);
   if (engine == MPINN_ENGINE_TCGEN05 && !ok) {
     *rc = fail("tcgen05 engine requested but the program is not supported by it");
     return false;
@@ -255,7 +255,7 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   if (e != cudaSuccess) return fail_cuda("device query", e);
   const int64_t n_pad = round_up64(n, 128);
   int rc;
-  if (use_tc(prog, d, order, engine, &rc)) {
+  if (stash != nullptr && use_tc(prog, d, order, engine, false, &rc)) {
     e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
                       info.sm_count, (cudaStream_t)stream);
   } else {
@@ -287,7 +287,7 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (e != cudaSuccess) return fail_cuda("device query", e);
   const int64_t n_pad = round_up64(n, 128);
   int rc;
-  if (use_tc(prog, d, order, engine, &rc)) {
+  if (use_tc(prog, d, order, engine, true, &rc)) {
     e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
                       n_pad, (float*)workspace, slabs, n_params, dparams, dx, info.sm_count,
                       (cudaStream_t)stream);
@@ -300,6 +300,14 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (e == cudaErrorInvalidConfiguration)
     return fail("layer widths too large for the shared-memory budget of this engine");
   if (e != cudaSuccess) return fail_cuda("jet_backward", e);
+  return 0;
+}
+
+int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream) {
+  if (!a || !b || !c) return fail("null pointer");
+  if (mode < 0 || mode > 3) return fail("mode must be 0..3");
+  cudaError_t e = launch_umma_selftest(mode, a, b, c, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("selftest_umma", e);
   return 0;
 }
 

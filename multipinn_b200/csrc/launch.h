@@ -18,7 +18,9 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
                             size_t smem_limit, cudaStream_t stream);
 
 // tcgen05 engine (jet_tc.cu)
-bool tc_supported(const DevProg& prog, int d, int order);
+bool tc_forward_supported(const DevProg& prog, int d, int order);
+bool tc_backward_supported(const DevProg& prog, int d, int order);
+cudaError_t launch_umma_selftest(int mode, const float* A, const float* B, float* C, cudaStream_t stream);
 cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float* packed,
                           const float* x, int64_t n, int d, int order, float* out, float* stash,
                           int64_t n_pad, int sm_count, cudaStream_t stream);

@@ -99,6 +99,10 @@ class CudaBackend:
         self._timed_end(tok)
         CudaBackend.gpu_launches += 2
 
+    def selftest_umma(self, mode, a, b, c):
+        _lib.check(self.lib.mpinn_selftest_umma(int(mode), self._ptr(a), self._ptr(b), self._ptr(c),
+                                                self._stream()), "mpinn_selftest_umma")
+
     def sumsq(self, r, accum):
         """accum (0-d / 1-elem fp32) += sum(r**2); r is a 1-D fp32 view with any stride."""
         assert r.dim() == 1 and r.is_cuda and r.dtype == torch.float32
@@ -241,7 +245,8 @@ class JetEngine:
         J = 1 + order * d
         out = torch.empty((J, n, self.n_out), dtype=torch.float32, device=x.device)
         stash = None
-        if need_stash:
+        if need_stash or (x.is_cuda and self.kernel_engine != _lib.ENGINE_FFMA):
+            # the tensor-core engine always round-trips pre-activations through this buffer (L2-hot)
             nbytes = b.stash_bytes(self.ops, d, order, n)
             stash = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=x.device)
         b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine)

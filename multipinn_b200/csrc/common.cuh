@@ -37,32 +37,52 @@ constexpr float kGeluC = 1.0f / 1.41421f;             // the reference's literal
 constexpr float kGeluC2 = kGeluC * kGeluC;
 constexpr float kInvSqrtPi = 0.5641895835477563f;
 
-// s0..s3 of the activation at z.  NEED3 selects whether the third derivative is produced.
+// The transcendental part of an activation at z, as two "basis" values from which s0..s3 follow with
+// a few FMAs:  GELU -> (Phi(z), phi(z)),  Sine -> (sin z, cos z).
+__device__ __forceinline__ void act_basis(int act, float z, float& P, float& Q) {
+  if (act == MPINN_ACT_GELU) {
+    const float cz = kGeluC * z;
+    P = 0.5f * (1.0f + erff(cz));
+    Q = (kGeluC * kInvSqrtPi) * expf(-(cz * cz));
+  } else if (act == MPINN_ACT_SINE) {
+    sincosf(z, &P, &Q);
+  } else {
+    P = 0.0f;
+    Q = 0.0f;
+  }
+}
+
+// s0..s3 of the activation at z from its basis values.  NEED3 selects whether s3 is produced.
 template <bool NEED3>
-__device__ __forceinline__ void act_coeffs(int act, float z, float& s0, float& s1, float& s2,
-                                           float& s3) {
+__device__ __forceinline__ void act_from_basis(int act, float z, float P, float Q, float& s0, float& s1,
+                                               float& s2, float& s3) {
   if (act == MPINN_ACT_GELU) {
     const float cz = kGeluC * z;
     const float cz2 = cz * cz;
-    const float Phi = 0.5f * (1.0f + erff(cz));
-    const float phi = (kGeluC * kInvSqrtPi) * expf(-cz2);
-    s0 = z * Phi;
-    s1 = fmaf(z, phi, Phi);
-    s2 = phi * (2.0f - 2.0f * cz2);
-    s3 = NEED3 ? (-2.0f * kGeluC2) * z * phi * (4.0f - 2.0f * cz2) : 0.0f;
+    s0 = z * P;
+    s1 = fmaf(z, Q, P);
+    s2 = Q * (2.0f - 2.0f * cz2);
+    s3 = NEED3 ? (-2.0f * kGeluC2) * z * Q * (4.0f - 2.0f * cz2) : 0.0f;
   } else if (act == MPINN_ACT_SINE) {
-    float s, c;
-    sincosf(z, &s, &c);
-    s0 = s;
-    s1 = c;
-    s2 = -s;
-    s3 = -c;
+    s0 = P;
+    s1 = Q;
+    s2 = -P;
+    s3 = -Q;
   } else {
     s0 = z;
     s1 = 1.0f;
     s2 = 0.0f;
     s3 = 0.0f;
   }
+}
+
+// s0..s3 of the activation at z.
+template <bool NEED3>
+__device__ __forceinline__ void act_coeffs(int act, float z, float& s0, float& s1, float& s2,
+                                           float& s3) {
+  float P, Q;
+  act_basis(act, z, P, Q);
+  act_from_basis<NEED3>(act, z, P, Q, s0, s1, s2, s3);
 }
 
 // forward activation jets, in place: z[J] -> a[J]

@@ -32,6 +32,16 @@ constexpr int kTcBlockFloats = 2 * kWTileBytes / 4;
 
 int64_t tc_block_floats(int width) { return width == kTcW ? kTcBlockFloats : 0; }
 
+constexpr int kBfRegion = kTileRows * 128;    // one bf16 piece of a [128 x 64] tile: 16 KiB
+constexpr int kBfTile = 4 * kBfRegion;        // piece1, piece2, piece3, ZERO region
+constexpr int kBfWRegion = kTcW * 128;        // one bf16 piece of a [64 x 64] weight operand: 8 KiB
+constexpr int kBfWTile = 3 * kBfWRegion;
+
+// byte offset of bf16 element (row, col<64) inside a swizzled region
+__host__ __device__ __forceinline__ uint32_t sw128_offset_bf16(int row, int col) {
+  return (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight packing: global image of the swizzled shared-memory operand tiles
 // ---------------------------------------------------------------------------------------------
@@ -52,11 +62,16 @@ __global__ void pack_tc_kernel(const __grid_constant__ DevProg prog, const float
       *reinterpret_cast<float*>(dst + off) = hi;
       *reinterpret_cast<float*>(dst + 2 * kWRegionBytes + off) = lo;
     }
-    // reverse operand: row n = in index, column k = o
+    // reverse operand (BF16x3, K-major): row n = in index, column k = o
     {
-      const uint32_t off = (uint32_t)(o / 32) * kWRegionBytes + sw128_offset(k, o % 32);
-      *reinterpret_cast<float*>(dst + kWTileBytes + off) = hi;
-      *reinterpret_cast<float*>(dst + kWTileBytes + 2 * kWRegionBytes + off) = lo;
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(w);
+      const float r1 = w - __bfloat162float(b1);
+      const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+      const uint32_t off = sw128_offset_bf16(k, o);
+      *reinterpret_cast<__nv_bfloat16*>(dst + kWTileBytes + off) = b1;
+      *reinterpret_cast<__nv_bfloat16*>(dst + kWTileBytes + kBfWRegion + off) = b2;
+      *reinterpret_cast<__nv_bfloat16*>(dst + kWTileBytes + 2 * kBfWRegion + off) = b3;
     }
   }
 }
@@ -93,38 +108,12 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_ti
   }
 }
 
-// dW-shaped product: D[128 x 64] (+)= [Zhi | Zlo]^T (features x points) * (Hhi + Hlo) (points x features)
-// Z and H tiles are [128 points x 64 features] hi/lo tiles viewed MN-major (K = points).
-// rows 0..63 of D: Zhi^T H, rows 64..127: Zlo^T H  (the caller adds the halves)
-__device__ __forceinline__ void issue_gemm_mnmajor(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
-                                                   uint32_t accumulate_first) {
-  constexpr uint32_t idesc = make_idesc_tf32(128, 64, 1, 1);
-  uint32_t acc = accumulate_first;
-#pragma unroll
-  for (int part = 0; part < 2; ++part) {                     // H_hi then H_lo
-    const uint32_t h_base = h_tile + part * 2 * kRegionBytes;
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {                        // 8 points per MMA
-      const uint32_t a_addr = z_tile + ks * 1024;            // 4 MN groups (hi kb0, hi kb1, lo kb0, lo kb1)
-      const uint32_t b_addr = h_base + ks * 1024;            // 2 MN groups (kb0, kb1)
-      mma_tf32_ss(d_tmem, make_desc_sw128(a_addr, kRegionBytes, 1024),
-                  make_desc_sw128(b_addr, kRegionBytes, 1024), idesc, acc);
-      acc = 1;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // BF16x3 operands (reverse pass).  a = a1 + a2 + a3 with three round-to-nearest bf16 pieces (24
 // mantissa bits); a product needs the six piece products whose weight is >= 2^-16.
 // A [rows x 64 features] piece is ONE 128B-swizzle region (row = 64 bf16 = 128 bytes), so the same
 // bytes are a K-major operand (K = features) and an MN-major operand (K = rows).
 // ---------------------------------------------------------------------------------------------
-constexpr int kBfRegion = kTileRows * 128;    // one piece of a [128 x 64] tile: 16 KiB
-constexpr int kBfTile = 4 * kBfRegion;        // piece1, piece2, piece3, ZERO region
-constexpr int kBfWRegion = kTcW * 128;        // one piece of a [64 x 64] weight operand: 8 KiB
-constexpr int kBfWTile = 3 * kBfWRegion;
-
 __device__ __forceinline__ void split_bf16x3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
   // two values at once: each piece packs (a, b) as a bf16x2 word, a in the low half
   const __nv_bfloat162 h1 = __floats2bfloat162_rn(a, b);
@@ -135,11 +124,6 @@ __device__ __forceinline__ void split_bf16x3(float a, float b, uint32_t& p1, uin
   p1 = *reinterpret_cast<const uint32_t*>(&h1);
   p2 = *reinterpret_cast<const uint32_t*>(&h2);
   p3 = *reinterpret_cast<const uint32_t*>(&h3);
-}
-
-// byte offset of bf16 element (row, col<64) inside a swizzled region
-__host__ __device__ __forceinline__ uint32_t sw128_offset_bf16(int row, int col) {
-  return (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
 }
 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
@@ -205,8 +189,9 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
 // ---------------------------------------------------------------------------------------------
 // self-test kernels (diagnostics for the descriptor/layout conventions)
 // ---------------------------------------------------------------------------------------------
-// mode 0: C[128][64] = A[128][64] * B[64][64]^T      (K-major path)
-// mode 1: C[128][64] = [Zhi|Zlo]^T H, Z=A[128][64], H=B2[128][64]  (MN-major path; host adds the halves)
+// mode 0: C[128][64] = A[128][64] * B[64][64]^T               3xTF32, K-major operands
+// mode 2: same product, BF16x3 K-major operands
+// mode 3: C[128][64] = stacked(A)^T B, A,B [128][64]          BF16x3 MN-major operands (host adds halves)
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ B, float* __restrict__ C) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -271,7 +256,6 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   const uint32_t tmem = tmem_base_s;
   if (t == 0) {
     if (mode == 0) issue_gemm_kmajor(tmem, smem_u32(a_tile), smem_u32(b_tile));
-    else if (mode == 1) issue_gemm_mnmajor(tmem, smem_u32(a_tile), smem_u32(b_tile), 0);
     else if (mode == 2) issue_bf16x3_kmajor(tmem, smem_u32(a_tile), smem_u32(b_tile));
     else issue_bf16x3_mnmajor(tmem, smem_u32(a_tile), smem_u32(b_tile), 0);
     mma_commit(&bar);
@@ -548,6 +532,387 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   if (th.warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// reverse
+// ---------------------------------------------------------------------------------------------
+// Per 128-point tile, walking the layers backwards.  For hidden layer l (64 -> 64) and jet channel j:
+//     zbar_j   = act'(z^l) applied to abar_j (abar lives in TMEM, left there by the previous GEMM)
+//     a_j      = activation jets of layer l-1, recomputed from the stash
+//     abar'_j  = zbar_j * W^l            tcgen05 BF16x3, K-major views     -> TMEM cols [64j, 64j+64)
+//     dW^l    += zbar_j^T * a_j          tcgen05 BF16x3, MN-major views of the SAME staged tiles
+// Channels are processed first-derivative, second-derivative (per direction), value last, so that every
+// abar_j is consumed before the GEMM that overwrites its TMEM columns is issued, and the value
+// channel's zbar can collect the cross terms of all directions.  The transcendental part of every
+// activation is evaluated once per (point, feature, layer) and kept as two basis values in shared memory.
+struct TcBwdSmem {
+  static constexpr int kZ = 0;                               // zbar tile: 3 pieces + ZERO   64 KiB
+  static constexpr int kH = kZ + kBfTile;                    // a tile: 3 pieces             48 KiB
+  static constexpr int kW = kH + 3 * kBfRegion;              // W^T operand, 3 pieces        24 KiB
+  static constexpr int kCache = kW + kBfWTile;               // basis values [2][64][128]    64 KiB
+  static constexpr int kRed = kCache + 2 * 64 * 128 * 4;     // [64][8] reduction scratch      2 KiB
+  static constexpr int kTotal = kRed + 64 * 8 * 4 + 1024;
+  static constexpr int kXchStride = 65;                      // dW half exchange aliases the a tile
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+template <int D, int ORDER>
+__global__ void __launch_bounds__(kTcThreads, 1)
+jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ params,
+           const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
+           const float* __restrict__ dout, const float* __restrict__ stash, int64_t n_pad,
+           float* __restrict__ part_all, int64_t n_params, int n_tiles) {
+  constexpr int J = 1 + ORDER * D;
+  constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* z_tile = smem + TcBwdSmem::kZ;
+  uint8_t* h_tile = smem + TcBwdSmem::kH;
+  uint8_t* w_tile = smem + TcBwdSmem::kW;
+  float* cache = reinterpret_cast<float*>(smem + TcBwdSmem::kCache);  // [2][64][128]
+  float* red_s = reinterpret_cast<float*>(smem + TcBwdSmem::kRed);    // [64][8]
+  float* xch = reinterpret_cast<float*>(h_tile);                      // [64][65] (only between GEMM groups)
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int t = threadIdx.x;
+  const int p = t % 128, fh = t / 128, warp = t / 32, lane = t % 32;
+  const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
+  const int f0 = fh * 32;
+
+  float* part = part_all + (int64_t)blockIdx.x * n_params;
+  for (int64_t i = t; i < n_params; i += kTcThreads) part[i] = 0.0f;
+  for (int i = t; i < kBfRegion / 16; i += kTcThreads)
+    reinterpret_cast<float4*>(z_tile + 3 * kBfRegion)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t == 0) {
+    mbar_init(&mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  uint32_t bar_phase = 0;
+  int pending = 0;
+  const int o = prog.n_out;
+  const int n_ops = prog.n_ops;
+
+  // fill the basis cache for (layer op, this thread's point and 32 features)
+  auto fill_cache = [&](const DevOp& op, int64_t pt) {
+    const float* z0p = stash + (int64_t)op.stash_plane * n_pad + pt;
+#pragma unroll 4
+    for (int ff = 0; ff < 32; ++ff) {
+      const int f = f0 + ff;
+      float P, Q;
+      act_basis(op.act, __ldg(z0p + (int64_t)f * n_pad), P, Q);
+      cache[f * 128 + p] = P;
+      cache[(64 + f) * 128 + p] = Q;
+    }
+  };
+  // sum a per-thread value over the warp's 32 points and add it to the CTA scratch row f, slot < 8
+  auto reduce_into = [&](float v, int f, int slot) {
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(&red_s[f * 8 + slot], v);
+  };
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t pt = (int64_t)tile * 128 + p;
+    const bool valid = pt < n;
+    float xv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
+
+    // =========================== output op (64 -> o), FMA pipe ===========================
+    {
+      const DevOp& op = prog.ops[n_ops - 1];
+      const DevOp& pv = prog.ops[n_ops - 2];
+      float dz[J][4];
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dz[j][k] = (valid && k < o) ? __ldg(dout + ((int64_t)j * n + pt) * o + k) : 0.0f;
+      for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
+      fill_cache(pv, pt);
+      __syncthreads();
+      const float* W = params + op.w_off;
+      const float* zp = stash + (int64_t)pv.stash_plane * n_pad + pt;
+      // abar^{L-1}_j[f] = sum_k W[k][f] dz[j][k]  -> TMEM, 8 features at a time
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            float a = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < o) a = fmaf(__ldg(W + k * kTcW + f), dz[j][k], a);
+            v[e] = a;
+          }
+          tmem_st8(tmem + lane_base + j * kTcW + f0 + c * 8, v);
+        }
+      }
+      // dW_last[k][f] += sum_pts sum_j dz[j][k] a_j[f] ; db_last[k] += sum_pts dz[0][k]
+#pragma unroll 2
+      for (int ff = 0; ff < 32; ++ff) {
+        const int f = f0 + ff;
+        float z[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) z[j] = __ldg(zp + (int64_t)(j * kTcW + f) * n_pad);
+        float s0, s1, s2, s3;
+        act_from_basis<false>(pv.act, z[0], cache[f * 128 + p], cache[(64 + f) * 128 + p], s0, s1, s2, s3);
+        float a[J];
+        a[0] = s0;
+        if (ORDER >= 1) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) a[1 + i] = s1 * z[1 + i];
+        }
+        if (ORDER >= 2) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) a[1 + D + i] = fmaf(s2 * z[1 + i], z[1 + i], s1 * z[1 + D + i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < o) {
+            float g = 0.0f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) g = fmaf(dz[j][k], a[j], g);
+            reduce_into(g, f, k);
+          }
+        }
+      }
+      if (fh == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < o) reduce_into(dz[0][k], k, 4);   // bias gradient rides in slot 4 of row k
+      }
+      __syncthreads();
+      for (int i = t; i < 64 * 4; i += kTcThreads) {
+        const int f = i / 4, k = i % 4;
+        if (k < o) part[op.w_off + k * kTcW + f] += red_s[f * 8 + k];
+      }
+      if (t < o) part[op.b_off + t] += red_s[t * 8 + 4];
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
+    }
+
+    // =========================== hidden layers, tensor cores ===========================
+    for (int l = n_ops - 2; l >= 1; --l) {
+      const DevOp& op = prog.ops[l];
+      const DevOp& pv = prog.ops[l - 1];
+      const float* zl = stash + (int64_t)op.stash_plane * n_pad + pt;    // z^l jets
+      const float* zm = stash + (int64_t)pv.stash_plane * n_pad + pt;    // z^{l-1} jets
+      // first three derivatives of layer l's activation for this thread's features, from the cached basis
+      float s1[32], s2[32], s3[32], acc0[32];
+#pragma unroll
+      for (int ff = 0; ff < 32; ++ff) {
+        const int f = f0 + ff;
+        float s0;
+        act_from_basis<(ORDER >= 2)>(op.act, __ldg(zl + (int64_t)f * n_pad), cache[f * 128 + p],
+                                     cache[(64 + f) * 128 + p], s0, s1[ff], s2[ff], s3[ff]);
+        acc0[ff] = 0.0f;
+      }
+      for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
+      __syncthreads();                 // everyone has read the layer-l basis
+      fill_cache(pv, pt);              // now the cache holds layer l-1
+      {
+        const float4* src = reinterpret_cast<const float4*>(
+            reinterpret_cast<const uint8_t*>(packed + op.tc_off) + kWTileBytes);
+        float4* dst = reinterpret_cast<float4*>(w_tile);
+        for (int i = t; i < kBfWTile / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+
+      uint32_t dw_acc = 0;
+      // channel schedule: (d/dx_i, d2/dx_i2) per direction, value channel last
+#pragma unroll
+      for (int step = 0; step < J; ++step) {
+        int jet;
+        if (step == J - 1) jet = 0;
+        else if (ORDER == 2) jet = (step & 1) ? 1 + D + (step >> 1) : 1 + (step >> 1);
+        else jet = 1 + step;
+        const bool is_first = (jet >= 1 && jet <= D);
+        const bool is_second = (jet > D);
+        const int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
+
+        if (pending) {
+          mbar_wait(&mma_bar, bar_phase);
+          bar_phase ^= 1;
+          pending = 0;
+        }
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
+          float ab[8], ab2[8], zb[8], av[8];
+          tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
+          if (is_first && ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ff = c * 8 + e;
+            const int f = f0 + ff;
+            // ---- zbar of layer l
+            if (jet == 0) {
+              zb[e] = fmaf(ab[e], s1[ff], acc0[ff]);
+            } else if (is_first) {
+              const float zi = __ldg(zl + (int64_t)(jet * kTcW + f) * n_pad);
+              float v = ab[e] * s1[ff];
+              float a0 = acc0[ff];
+              a0 = fmaf(ab[e] * s2[ff], zi, a0);
+              if (ORDER == 2) {
+                const float zii = __ldg(zl + (int64_t)((1 + D + dir) * kTcW + f) * n_pad);
+                v = fmaf(2.0f * ab2[e] * s2[ff], zi, v);
+                a0 = fmaf(ab2[e], fmaf(s3[ff] * zi, zi, s2[ff] * zii), a0);
+              }
+              acc0[ff] = a0;
+              zb[e] = v;
+            } else {
+              zb[e] = ab[e] * s1[ff];
+            }
+            // ---- activation jet channel of layer l-1
+            const float z0 = __ldg(zm + (int64_t)f * n_pad);
+            float t0, t1, t2, t3;
+            act_from_basis<false>(pv.act, z0, cache[f * 128 + p], cache[(64 + f) * 128 + p], t0, t1, t2, t3);
+            if (jet == 0) {
+              av[e] = t0;
+            } else if (is_first) {
+              av[e] = t1 * __ldg(zm + (int64_t)(jet * kTcW + f) * n_pad);
+            } else {
+              const float zi = __ldg(zm + (int64_t)((1 + dir) * kTcW + f) * n_pad);
+              const float zii = __ldg(zm + (int64_t)(jet * kTcW + f) * n_pad);
+              av[e] = fmaf(t2 * zi, zi, t1 * zii);
+            }
+          }
+          if (jet == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) reduce_into(zb[e], f0 + c * 8 + e, 0);   // bias gradient of layer l
+          }
+          uint32_t zq[3][4], aq[3][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            split_bf16x3(zb[2 * e], zb[2 * e + 1], zq[0][e], zq[1][e], zq[2][e]);
+            split_bf16x3(av[2 * e], av[2 * e + 1], aq[0][e], aq[1][e], aq[2][e]);
+          }
+          const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<uint4*>(z_tile + q * kBfRegion + off) = make_uint4(zq[q][0], zq[q][1], zq[q][2], zq[q][3]);
+            *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(aq[q][0], aq[q][1], aq[q][2], aq[q][3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+          tc_fence_after_sync();
+          issue_bf16x3_kmajor(tmem + jet * kTcW, smem_u32(z_tile), smem_u32(w_tile));
+          issue_bf16x3_mnmajor(tmem + kDwCol, smem_u32(z_tile), smem_u32(h_tile), dw_acc);
+          mma_commit(&mma_bar);
+        }
+        dw_acc = 1;
+        pending = 1;
+      }
+      mbar_wait(&mma_bar, bar_phase);
+      bar_phase ^= 1;
+      pending = 0;
+      tc_fence_after_sync();
+      // ---- flush this (tile, layer)'s dW: rows 64..127 of the accumulator fold onto rows 0..63
+      if ((warp % 4) >= 2) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + kDwCol + f0, v);
+        const int row = (warp % 4) * 32 + lane - 64;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) xch[row * TcBwdSmem::kXchStride + f0 + c] = v[c];
+      }
+      __syncthreads();
+      if ((warp % 4) < 2) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + kDwCol + f0, v);
+        const int row = (warp % 4) * 32 + lane;
+        float* dst = part + op.w_off + row * kTcW + f0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) dst[c] += v[c] + xch[row * TcBwdSmem::kXchStride + f0 + c];
+      }
+      if (t < 64) part[op.b_off + t] += red_s[t * 8 + 0];
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
+    }
+
+    // =========================== op 0 (d -> 64), FMA pipe ===========================
+    {
+      const DevOp& op = prog.ops[0];
+      const float* z0p = stash + (int64_t)op.stash_plane * n_pad + pt;
+      for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float ab0[8], zb0[8];
+        tmem_ld8(tmem + lane_base + f0 + c * 8, ab0);
+        float s1[8], s2[8], s3[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int f = f0 + c * 8 + e;
+          float s0;
+          act_from_basis<(ORDER >= 2)>(op.act, __ldg(z0p + (int64_t)f * n_pad), cache[f * 128 + p],
+                                       cache[(64 + f) * 128 + p], s0, s1[e], s2[e], s3[e]);
+          zb0[e] = ab0[e] * s1[e];
+        }
+        if (ORDER >= 1) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            float abi[8], abii[8];
+            tmem_ld8(tmem + lane_base + (1 + i) * kTcW + f0 + c * 8, abi);
+            if (ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + i) * kTcW + f0 + c * 8, abii);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              const float zi = __ldg(z0p + (int64_t)((1 + i) * kTcW + f) * n_pad);
+              float zbi = abi[e] * s1[e];
+              zb0[e] = fmaf(abi[e] * s2[e], zi, zb0[e]);
+              if (ORDER == 2) {
+                const float zii = __ldg(z0p + (int64_t)((1 + D + i) * kTcW + f) * n_pad);
+                zbi = fmaf(2.0f * abii[e] * s2[e], zi, zbi);
+                zb0[e] = fmaf(abii[e], fmaf(s3[e] * zi, zi, s2[e] * zii), zb0[e]);
+              }
+              reduce_into(zbi, f, 1 + i);     // d z_i / d W[f][i] = 1
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int f = f0 + c * 8 + e;
+          reduce_into(zb0[e], f, 0);          // bias
+#pragma unroll
+          for (int i = 0; i < D; ++i) reduce_into(zb0[e] * xv[i], f, 4 + i);
+        }
+      }
+      __syncthreads();
+      for (int i = t; i < 64 * D; i += kTcThreads) {
+        const int f = i / D, k = i % D;
+        part[op.w_off + f * D + k] += red_s[f * 8 + 4 + k] + (ORDER >= 1 ? red_s[f * 8 + 1 + k] : 0.0f);
+      }
+      if (t < 64) part[op.b_off + t] += red_s[t * 8 + 0];
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -567,7 +932,9 @@ bool tc_forward_supported(const DevProg& prog, int d, int order) {
   return last.kind == MPINN_OP_LINEAR && last.in_dim == kTcW && last.act == MPINN_ACT_NONE && !last.flags;
 }
 
-bool tc_backward_supported(const DevProg&, int, int) { return false; }
+bool tc_backward_supported(const DevProg& prog, int d, int order) {
+  return tc_forward_supported(prog, d, order);
+}
 
 template <int D, int ORDER>
 static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, const float* packed,
@@ -596,12 +963,49 @@ cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float*
   return cudaErrorInvalidValue;
 }
 
+// dparams[i] += sum_c part[c][i]  (same fold as the FFMA engine)
+__global__ void fold_partials_tc(const float* __restrict__ part, int n_slabs, int64_t n_params,
+                                 float* __restrict__ dparams) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_params) return;
+  float s = 0.0f;
+  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * n_params + i];
+  dparams[i] += s;
+}
+
+template <int D, int ORDER>
+static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, const float* packed,
+                                   const float* x, int64_t n, const float* dout, const float* stash,
+                                   int64_t n_pad, float* part, int max_slabs, int64_t n_params,
+                                   float* dparams, int sm_count, cudaStream_t stream) {
+  auto kern = jet_bwd_tc<D, ORDER>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdSmem::kTotal);
+  if (e != cudaSuccess) return e;
+  const int n_tiles = (int)((n + 127) / 128);
+  int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  if (grid > max_slabs) grid = max_slabs;
+  kern<<<grid, kTcThreads, TcBwdSmem::kTotal, stream>>>(prog, params, packed, x, n, dout, stash, n_pad, part,
+                                                         n_params, n_tiles);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  fold_partials_tc<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, dparams);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float* packed, const float* x,
                           int64_t n, int d, int order, const float* dout, const float* stash, int64_t n_pad,
                           float* part, int max_slabs, int64_t n_params, float* dparams, float* dx,
                           int sm_count, cudaStream_t stream) {
-  (void)sm_count;
-  return cudaErrorNotSupported;
+  if (dx != nullptr) return cudaErrorNotSupported;
+#define TC_BWD(D_, O_) \
+  if (d == D_ && order == O_) \
+    return launch_bwd_tc_t<D_, O_>(prog, params, packed, x, n, dout, stash, n_pad, part, max_slabs, \
+                                   n_params, dparams, sm_count, stream)
+  TC_BWD(1, 0); TC_BWD(1, 1); TC_BWD(1, 2);
+  TC_BWD(2, 0); TC_BWD(2, 1); TC_BWD(2, 2);
+  TC_BWD(3, 0); TC_BWD(3, 1); TC_BWD(3, 2);
+#undef TC_BWD
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace mpinn

@@ -21,7 +21,8 @@ namespace mpinn {
 using namespace umma;
 
 constexpr int kTcW = 64;                 // layer width handled by this engine
-constexpr int kTcThreads = 256;          // 8 warps: 2 threads per point
+constexpr int kTcThreads = 512;          // 16 warps: 4 threads per point, 16 features each
+constexpr int kFpt = kTcW / (kTcThreads / 128);  // features per thread
 constexpr int kTileRows = 128;
 constexpr int kRegionBytes = kTileRows * 128;       // [128 rows x 32 fp32]  = 16 KiB
 constexpr int kATileBytes = 4 * kRegionBytes;       // hi kb0, hi kb1, lo kb0, lo kb1 = 64 KiB
@@ -290,14 +291,8 @@ struct TcSmem {
   static constexpr int kA1 = kATileBytes;
   static constexpr int kW = 2 * kATileBytes;
   static constexpr int kBias = kW + kWTileBytes;            // 64 floats
-  static constexpr int kRed = kBias + 256;                  // 128 points x 8 floats scratch
-  static constexpr int kTotal = kRed + 128 * 8 * 4 + 1024;  // + alignment slack
-};
-
-// which TMEM quarter / point / feature half a thread owns
-struct TcThread {
-  int p, fh, warp;
-  uint32_t lane_base;  // TMEM lane field for tcgen05.ld/st issued by this warp
+  static constexpr int kRed = kBias + 256;                  // [3 quarters][128 points][8] floats scratch
+  static constexpr int kTotal = kRed + 3 * 128 * 8 * 4 + 1024;  // + alignment slack
 };
 
 template <int D, int ORDER>
@@ -311,39 +306,40 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   uint8_t* a_buf[2] = {smem + TcSmem::kA0, smem + TcSmem::kA1};
   uint8_t* w_buf = smem + TcSmem::kW;
   float* bias_s = reinterpret_cast<float*>(smem + TcSmem::kBias);
-  float* red_s = reinterpret_cast<float*>(smem + TcSmem::kRed);
+  float* red_s = reinterpret_cast<float*>(smem + TcSmem::kRed);   // [3][128][8]
   __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x;
-  TcThread th;
-  th.p = t % 128;
-  th.fh = t / 128;
-  th.warp = t / 32;
-  th.lane_base = (uint32_t)((th.warp % 4) * 32) << 16;
+  const int p = t % 128, fq = t / 128, warp = t / 32;
+  const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
+  const int f0 = fq * kFpt;                                   // first feature of this thread
+  // byte offset of this thread's first 16-byte chunk inside an operand tile (K block, row, column)
+  const uint32_t tile_kb = (uint32_t)(f0 / 32) * kRegionBytes;
+  const int col0 = f0 % 32;
 
   if (t == 0) {
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
     fence_mbar_init();
   }
-  if (th.warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  uint32_t bar_phase[2] = {0, 0};   // parity of the next completion to wait for, per A buffer
-  int pending[2] = {0, 0};          // an MMA group is in flight on that buffer
-
+  uint32_t bar_phase0 = 0, bar_phase1 = 0;   // parity of the next completion to wait for, per A buffer
+  int pending0 = 0, pending1 = 0;            // an MMA group is in flight on that buffer
   const int o = prog.n_out;
-  const int f0 = th.fh * 32;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t pt = (int64_t)tile * 128 + th.p;
+    const int64_t pt = (int64_t)tile * 128 + p;
     const bool valid = pt < n;
     float xv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
+    // this tile's block of the stash: [plane][128 points], this thread's point
+    float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;
 
     // ---- op 0: LINEAR(d -> 64) on the FMA pipe: z = W x + b, z_i = W[:, i], z_ii = 0  -> stash
     {
@@ -351,7 +347,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const float* W = params + op.w_off;
       const float* b = params + op.b_off;
 #pragma unroll 4
-      for (int ff = 0; ff < 32; ++ff) {
+      for (int ff = 0; ff < kFpt; ++ff) {
         const int f = f0 + ff;
         float z0 = __ldg(b + f);
         float w[D];
@@ -360,80 +356,77 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           w[i] = __ldg(W + f * D + i);
           z0 = fmaf(w[i], xv[i], z0);
         }
-        float* sp = stash + (int64_t)(op.stash_plane + f) * n_pad + pt;
+        float* sp = tstash + (op.stash_plane + f) * 128;
         sp[0] = z0;
         if (ORDER >= 1) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) sp[(int64_t)(1 + i) * kTcW * n_pad] = w[i];
+          for (int i = 0; i < D; ++i) sp[(1 + i) * kTcW * 128] = w[i];
         }
         if (ORDER >= 2) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) sp[(int64_t)(1 + D + i) * kTcW * n_pad] = 0.0f;
+          for (int i = 0; i < D; ++i) sp[(1 + D + i) * kTcW * 128] = 0.0f;
         }
       }
     }
-    __syncthreads();  // stash planes of this tile are written by both feature halves
+    __syncthreads();
 
     // ---- hidden GEMM layers
     for (int l = 1; l < prog.n_ops - 1; ++l) {
       const DevOp& op = prog.ops[l];
       const DevOp& pv = prog.ops[l - 1];
-      // make sure no MMA still reads the weight tile, then load this layer's operand + bias
-      for (int b = 0; b < 2; ++b) {
-        if (pending[b]) {
-          mbar_wait(&mma_bar[b], bar_phase[b]);
-          bar_phase[b] ^= 1;
-          pending[b] = 0;
-        }
-      }
       {
         const float4* src = reinterpret_cast<const float4*>(packed + op.tc_off);
         float4* dst = reinterpret_cast<float4*>(w_buf);
         for (int i = t; i < kWTileBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
         if (t < kTcW) bias_s[t] = __ldg(params + op.b_off + t);
       }
-      // sigma'(z0), sigma''(z0) of the previous layer for this thread's 32 features
-      float s1[32], s2[32];
-      const float* zprev = stash + (int64_t)pv.stash_plane * n_pad + pt;
-#pragma unroll
+      // first and second derivative of the previous layer's activation, this thread's features
+      float s1[kFpt], s2[kFpt];
+      const float* zprev = tstash + pv.stash_plane * 128;
+#pragma unroll 1
       for (int j = 0; j < J; ++j) {
         const int buf = j & 1;
-        if (pending[buf]) {
-          mbar_wait(&mma_bar[buf], bar_phase[buf]);
-          bar_phase[buf] ^= 1;
-          pending[buf] = 0;
+        if (buf == 0 ? pending0 : pending1) {
+          if (buf == 0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
+          else          { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
         }
         uint8_t* at = a_buf[buf];
-        // prologue: activation jet channel j of the previous layer for (point, 32 features)
+        // which stash planes this channel needs: z_j, and z_i again for a second-derivative channel
+        const int ji = (j > D) ? j - D : j;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {     // 8 chunks of 4 features = one 16-byte store each (hi and lo)
-          float hi4[4], lo4[4];
+        for (int c = 0; c < kFpt / 8; ++c) {     // 8 features: all loads first, then the math
+          float za[8], zb[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int ff = q * 4 + e;
-            const int f = f0 + ff;
-            float a;
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            za[e] = __ldcg(zprev + (ji * kTcW + f) * 128);
+            zb[e] = (j > D) ? __ldcg(zprev + (j * kTcW + f) * 128) : 0.0f;
+          }
+          float a[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ff = c * 8 + e;
             if (j == 0) {
-              const float z0 = __ldcg(zprev + (int64_t)f * n_pad);
               float c0, c1, c2, c3;
-              act_coeffs<false>(pv.act, z0, c0, c1, c2, c3);
+              act_coeffs<false>(pv.act, za[e], c0, c1, c2, c3);
               s1[ff] = c1;
               s2[ff] = c2;
-              a = c0;
+              a[e] = c0;
             } else if (j <= D) {
-              const float zi = __ldcg(zprev + (int64_t)(j * kTcW + f) * n_pad);
-              a = s1[ff] * zi;
+              a[e] = s1[ff] * za[e];
             } else {
-              const float zi = __ldcg(zprev + (int64_t)((j - D) * kTcW + f) * n_pad);
-              const float zii = __ldcg(zprev + (int64_t)(j * kTcW + f) * n_pad);
-              a = fmaf(s2[ff] * zi, zi, s1[ff] * zii);
+              a[e] = fmaf(s2[ff] * za[e], za[e], s1[ff] * zb[e]);
             }
-            split_tf32(a, hi4[e], lo4[e]);
           }
-          const int col = q * 4;  // column inside the 32-feature K block owned by this thread half
-          const uint32_t off = (uint32_t)th.fh * kRegionBytes + sw128_offset(th.p, col);
-          *reinterpret_cast<float4*>(at + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
-          *reinterpret_cast<float4*>(at + 2 * kRegionBytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {          // two 16-byte chunks (4 fp32 each) per 8 features
+            float hi4[4], lo4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32(a[h * 4 + e], hi4[e], lo4[e]);
+            const uint32_t off = tile_kb + sw128_offset(p, col0 + c * 8 + h * 4);
+            *reinterpret_cast<float4*>(at + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+            *reinterpret_cast<float4*>(at + 2 * kRegionBytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
@@ -443,28 +436,26 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           issue_gemm_kmajor(tmem + j * kTcW, smem_u32(at), smem_u32(w_buf));
           mma_commit(&mma_bar[buf]);
         }
-        pending[buf] = 1;
+        if (buf == 0) pending0 = 1; else pending1 = 1;
       }
-      // wait for all channels
-      for (int b = 0; b < 2; ++b) {
-        if (pending[b]) {
-          mbar_wait(&mma_bar[b], bar_phase[b]);
-          bar_phase[b] ^= 1;
-          pending[b] = 0;
-        }
-      }
+      if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
+      if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
       tc_fence_after_sync();
       // epilogue: z = D + b  -> stash (the next layer's prologue, or the output layer, reads it back)
-      float* zout = stash + (int64_t)op.stash_plane * n_pad + pt;
-#pragma unroll
+      float* zout = tstash + op.stash_plane * 128;
+#pragma unroll 1
       for (int j = 0; j < J; ++j) {
-        float v[32];
-        tmem_ld32(tmem + th.lane_base + j * kTcW + f0, v);
 #pragma unroll
-        for (int ff = 0; ff < 32; ++ff) {
-          float z = v[ff];
-          if (j == 0) z += bias_s[f0 + ff];
-          zout[(int64_t)(j * kTcW + f0 + ff) * n_pad] = z;
+        for (int c = 0; c < kFpt / 8; ++c) {
+          float v[8];
+          tmem_ld8(tmem + lane_base + j * kTcW + f0 + c * 8, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            float z = v[e];
+            if (j == 0) z += bias_s[f];
+            zout[(j * kTcW + f) * 128] = z;
+          }
         }
       }
       tc_fence_before_sync();
@@ -476,18 +467,18 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const DevOp& op = prog.ops[prog.n_ops - 1];
       const DevOp& pv = prog.ops[prog.n_ops - 2];
       const float* W = params + op.w_off;
-      const float* zprev = stash + (int64_t)pv.stash_plane * n_pad + pt;
+      const float* zprev = tstash + pv.stash_plane * 128;
       float acc[J][4];
 #pragma unroll
       for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[j][k] = 0.0f;
 #pragma unroll 2
-      for (int ff = 0; ff < 32; ++ff) {
+      for (int ff = 0; ff < kFpt; ++ff) {
         const int f = f0 + ff;
         float z[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) z[j] = __ldcg(zprev + (int64_t)(j * kTcW + f) * n_pad);
+        for (int j = 0; j < J; ++j) z[j] = __ldcg(zprev + (j * kTcW + f) * 128);
         act_jets<D, ORDER>(pv.act, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -498,26 +489,27 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
         }
       }
-      // combine the two feature halves of each point through shared memory
+      // combine the feature quarters of each point through shared memory, 8 outputs at a time
       for (int base = 0; base < J * o; base += 8) {
-        if (th.fh == 1) {
+        if (fq > 0) {
 #pragma unroll
           for (int j = 0; j < J; ++j)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int idx = j * o + k - base;
-              if (k < o && idx >= 0 && idx < 8) red_s[th.p * 8 + idx] = acc[j][k];
+              if (k < o && idx >= 0 && idx < 8) red_s[((fq - 1) * 128 + p) * 8 + idx] = acc[j][k];
             }
         }
         __syncthreads();
-        if (th.fh == 0 && valid) {
+        if (fq == 0 && valid) {
 #pragma unroll
           for (int j = 0; j < J; ++j)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int idx = j * o + k - base;
               if (k < o && idx >= 0 && idx < 8) {
-                float v = acc[j][k] + red_s[th.p * 8 + idx];
+                float v = acc[j][k];
+                for (int q = 0; q < kTcThreads / 128 - 1; ++q) v += red_s[(q * 128 + p) * 8 + idx];
                 if (j == 0) v += __ldg(params + op.b_off + k);
                 out[((int64_t)j * n + pt) * o + k] = v;
               }
@@ -529,9 +521,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (th.warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // reverse
@@ -555,6 +546,11 @@ struct TcBwdSmem {
   static constexpr int kXchStride = 65;                      // dW half exchange aliases the a tile
 };
 
+// one thread asks the L2 to fetch `bytes` (multiple of 16) starting at p
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -569,6 +565,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
            float* __restrict__ part_all, int64_t n_params, int n_tiles) {
   constexpr int J = 1 + ORDER * D;
   constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
+  constexpr int NC = kFpt / 8;      // 8-feature chunks per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* z_tile = smem + TcBwdSmem::kZ;
@@ -581,9 +578,9 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x;
-  const int p = t % 128, fh = t / 128, warp = t / 32, lane = t % 32;
+  const int p = t % 128, fq = t / 128, warp = t / 32, lane = t % 32;
   const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
-  const int f0 = fh * 32;
+  const int f0 = fq * kFpt;
 
   float* part = part_all + (int64_t)blockIdx.x * n_params;
   for (int64_t i = t; i < n_params; i += kTcThreads) part[i] = 0.0f;
@@ -604,16 +601,22 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   const int o = prog.n_out;
   const int n_ops = prog.n_ops;
 
-  // fill the basis cache for (layer op, this thread's point and 32 features)
-  auto fill_cache = [&](const DevOp& op, int64_t pt) {
-    const float* z0p = stash + (int64_t)op.stash_plane * n_pad + pt;
-#pragma unroll 4
-    for (int ff = 0; ff < 32; ++ff) {
-      const int f = f0 + ff;
-      float P, Q;
-      act_basis(op.act, __ldg(z0p + (int64_t)f * n_pad), P, Q);
-      cache[f * 128 + p] = P;
-      cache[(64 + f) * 128 + p] = Q;
+  // fill the basis cache for (layer op, this thread's point and features)
+  auto fill_cache = [&](const DevOp& op, const float* tstash) {
+    const float* z0p = tstash + op.stash_plane * 128;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float z[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[e] = __ldg(z0p + (f0 + c * 8 + e) * 128);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int f = f0 + c * 8 + e;
+        float P, Q;
+        act_basis(op.act, z[e], P, Q);
+        cache[f * 128 + p] = P;
+        cache[(64 + f) * 128 + p] = Q;
+      }
     }
   };
   // sum a per-thread value over the warp's 32 points and add it to the CTA scratch row f, slot < 8
@@ -629,6 +632,13 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
 
+    const float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;
+    if (t == 0 && tile == (int)blockIdx.x) {
+      // first tile of this CTA: the two stash blocks the first hidden iteration reads
+      l2_prefetch_bulk(tstash - p + prog.ops[n_ops - 2].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
+      if (n_ops >= 4) l2_prefetch_bulk(tstash - p + prog.ops[n_ops - 3].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
+    }
+
     // =========================== output op (64 -> o), FMA pipe ===========================
     {
       const DevOp& op = prog.ops[n_ops - 1];
@@ -640,15 +650,15 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         for (int k = 0; k < 4; ++k)
           dz[j][k] = (valid && k < o) ? __ldg(dout + ((int64_t)j * n + pt) * o + k) : 0.0f;
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
-      fill_cache(pv, pt);
+      fill_cache(pv, tstash);
       __syncthreads();
       const float* W = params + op.w_off;
-      const float* zp = stash + (int64_t)pv.stash_plane * n_pad + pt;
+      const float* zp = tstash + pv.stash_plane * 128;
       // abar^{L-1}_j[f] = sum_k W[k][f] dz[j][k]  -> TMEM, 8 features at a time
 #pragma unroll
       for (int j = 0; j < J; ++j) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -664,11 +674,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       }
       // dW_last[k][f] += sum_pts sum_j dz[j][k] a_j[f] ; db_last[k] += sum_pts dz[0][k]
 #pragma unroll 2
-      for (int ff = 0; ff < 32; ++ff) {
+      for (int ff = 0; ff < kFpt; ++ff) {
         const int f = f0 + ff;
         float z[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) z[j] = __ldg(zp + (int64_t)(j * kTcW + f) * n_pad);
+        for (int j = 0; j < J; ++j) z[j] = __ldg(zp + (j * kTcW + f) * 128);
         float s0, s1, s2, s3;
         act_from_basis<false>(pv.act, z[0], cache[f * 128 + p], cache[(64 + f) * 128 + p], s0, s1, s2, s3);
         float a[J];
@@ -691,7 +701,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
         }
       }
-      if (fh == 0) {
+      if (fq == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k < o) reduce_into(dz[0][k], k, 4);   // bias gradient rides in slot 4 of row k
@@ -711,21 +721,27 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     for (int l = n_ops - 2; l >= 1; --l) {
       const DevOp& op = prog.ops[l];
       const DevOp& pv = prog.ops[l - 1];
-      const float* zl = stash + (int64_t)op.stash_plane * n_pad + pt;    // z^l jets
-      const float* zm = stash + (int64_t)pv.stash_plane * n_pad + pt;    // z^{l-1} jets
+      const float* zl = tstash + op.stash_plane * 128;    // z^l jets
+      const float* zm = tstash + pv.stash_plane * 128;    // z^{l-1} jets
       // first three derivatives of layer l's activation for this thread's features, from the cached basis
-      float s1[32], s2[32], s3[32], acc0[32];
+      float s1[kFpt], s2[kFpt], s3[kFpt], acc0[kFpt];
 #pragma unroll
-      for (int ff = 0; ff < 32; ++ff) {
-        const int f = f0 + ff;
-        float s0;
-        act_from_basis<(ORDER >= 2)>(op.act, __ldg(zl + (int64_t)f * n_pad), cache[f * 128 + p],
-                                     cache[(64 + f) * 128 + p], s0, s1[ff], s2[ff], s3[ff]);
-        acc0[ff] = 0.0f;
+      for (int c = 0; c < NC; ++c) {
+        float z[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = __ldg(zl + (f0 + c * 8 + e) * 128);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ff = c * 8 + e, f = f0 + ff;
+          float s0;
+          act_from_basis<(ORDER >= 2)>(op.act, z[e], cache[f * 128 + p], cache[(64 + f) * 128 + p], s0,
+                                       s1[ff], s2[ff], s3[ff]);
+          acc0[ff] = 0.0f;
+        }
       }
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
       __syncthreads();                 // everyone has read the layer-l basis
-      fill_cache(pv, pt);              // now the cache holds layer l-1
+      fill_cache(pv, tstash);          // now the cache holds layer l-1
       {
         const float4* src = reinterpret_cast<const float4*>(
             reinterpret_cast<const uint8_t*>(packed + op.tc_off) + kWTileBytes);
@@ -734,9 +750,20 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       }
       __syncthreads();
 
+      // the layer below will be needed next (its z as "z^l", and the one under it as "z^{l-1}"):
+      // pull that tile-layer block (J*64 planes x 512 B, contiguous) into L2 while this layer computes
+      if (t == 0 && l >= 2) {
+        const DevOp& nx = prog.ops[l - 2];
+        l2_prefetch_bulk(tstash - p + nx.stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
+      }
+      if (t == 0 && l == 1 && tile + (int)gridDim.x < n_tiles) {   // next tile's two top blocks
+        const float* nt = stash + (int64_t)(tile + gridDim.x) * prog.total_planes * 128;
+        l2_prefetch_bulk(nt + prog.ops[n_ops - 2].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
+        if (n_ops >= 4) l2_prefetch_bulk(nt + prog.ops[n_ops - 3].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
+      }
       uint32_t dw_acc = 0;
       // channel schedule: (d/dx_i, d2/dx_i2) per direction, value channel last
-#pragma unroll
+#pragma unroll 1
       for (int step = 0; step < J; ++step) {
         int jet;
         if (step == J - 1) jet = 0;
@@ -745,6 +772,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         const bool is_first = (jet >= 1 && jet <= D);
         const bool is_second = (jet > D);
         const int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
+        const bool two = is_first && ORDER == 2;
 
         if (pending) {
           mbar_wait(&mma_bar, bar_phase);
@@ -753,61 +781,71 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
         tc_fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
-          float ab[8], ab2[8], zb[8], av[8];
-          tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
-          if (is_first && ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ff = c * 8 + e;
-            const int f = f0 + ff;
-            // ---- zbar of layer l
-            if (jet == 0) {
-              zb[e] = fmaf(ab[e], s1[ff], acc0[ff]);
-            } else if (is_first) {
-              const float zi = __ldg(zl + (int64_t)(jet * kTcW + f) * n_pad);
-              float v = ab[e] * s1[ff];
-              float a0 = acc0[ff];
-              a0 = fmaf(ab[e] * s2[ff], zi, a0);
-              if (ORDER == 2) {
-                const float zii = __ldg(zl + (int64_t)((1 + D + dir) * kTcW + f) * n_pad);
-                v = fmaf(2.0f * ab2[e] * s2[ff], zi, v);
-                a0 = fmaf(ab2[e], fmaf(s3[ff] * zi, zi, s2[ff] * zii), a0);
-              }
-              acc0[ff] = a0;
-              zb[e] = v;
-            } else {
-              zb[e] = ab[e] * s1[ff];
-            }
-            // ---- activation jet channel of layer l-1
-            const float z0 = __ldg(zm + (int64_t)f * n_pad);
-            float t0, t1, t2, t3;
-            act_from_basis<false>(pv.act, z0, cache[f * 128 + p], cache[(64 + f) * 128 + p], t0, t1, t2, t3);
-            if (jet == 0) {
-              av[e] = t0;
-            } else if (is_first) {
-              av[e] = t1 * __ldg(zm + (int64_t)(jet * kTcW + f) * n_pad);
-            } else {
-              const float zi = __ldg(zm + (int64_t)((1 + dir) * kTcW + f) * n_pad);
-              const float zii = __ldg(zm + (int64_t)(jet * kTcW + f) * n_pad);
-              av[e] = fmaf(t2 * zi, zi, t1 * zii);
-            }
-          }
-          if (jet == 0) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) reduce_into(zb[e], f0 + c * 8 + e, 0);   // bias gradient of layer l
-          }
-          uint32_t zq[3][4], aq[3][4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            split_bf16x3(zb[2 * e], zb[2 * e + 1], zq[0][e], zq[1][e], zq[2][e]);
-            split_bf16x3(av[2 * e], av[2 * e + 1], aq[0][e], aq[1][e], aq[2][e]);
-          }
+        for (int c = 0; c < NC; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
           const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
+          // ---------------- zbar of layer l ----------------
+          {
+            float ab[8], ab2[8], zi[8], zii[8], zb[8];
+            tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
+            if (two) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            *reinterpret_cast<uint4*>(z_tile + q * kBfRegion + off) = make_uint4(zq[q][0], zq[q][1], zq[q][2], zq[q][3]);
-            *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(aq[q][0], aq[q][1], aq[q][2], aq[q][3]);
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              zi[e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
+              zii[e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ff = c * 8 + e;
+              if (jet == 0) {
+                zb[e] = fmaf(ab[e], s1[ff], acc0[ff]);
+              } else if (is_first) {
+                float v = ab[e] * s1[ff];
+                float a0 = fmaf(ab[e] * s2[ff], zi[e], acc0[ff]);
+                if (ORDER == 2) {
+                  v = fmaf(2.0f * ab2[e] * s2[ff], zi[e], v);
+                  a0 = fmaf(ab2[e], fmaf(s3[ff] * zi[e], zi[e], s2[ff] * zii[e]), a0);
+                }
+                acc0[ff] = a0;
+                zb[e] = v;
+              } else {
+                zb[e] = ab[e] * s1[ff];
+              }
+            }
+            if (jet == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) reduce_into(zb[e], f0 + c * 8 + e, 0);   // bias gradient of layer l
+            }
+            uint32_t q1[4], q2[4], q3[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16x3(zb[2 * e], zb[2 * e + 1], q1[e], q2[e], q3[e]);
+            *reinterpret_cast<uint4*>(z_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+            *reinterpret_cast<uint4*>(z_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+            *reinterpret_cast<uint4*>(z_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+          }
+          // ---------------- activation jet channel of layer l-1 ----------------
+          {
+            float y0[8], yi[8], yii[8], av[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              y0[e] = __ldg(zm + f * 128);
+              yi[e] = (jet != 0) ? __ldg(zm + ((1 + dir) * kTcW + f) * 128) : 0.0f;
+              yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              float t0, t1, t2, t3;
+              act_from_basis<false>(pv.act, y0[e], cache[f * 128 + p], cache[(64 + f) * 128 + p], t0, t1, t2, t3);
+              av[e] = (jet == 0) ? t0 : (is_first ? t1 * yi[e] : fmaf(t2 * yi[e], yi[e], t1 * yii[e]));
+            }
+            uint32_t q1[4], q2[4], q3[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16x3(av[2 * e], av[2 * e + 1], q1[e], q2[e], q3[e]);
+            *reinterpret_cast<uint4*>(h_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+            *reinterpret_cast<uint4*>(h_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+            *reinterpret_cast<uint4*>(h_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
           }
         }
         fence_proxy_async_smem();
@@ -828,20 +866,32 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       tc_fence_after_sync();
       // ---- flush this (tile, layer)'s dW: rows 64..127 of the accumulator fold onto rows 0..63
       if ((warp % 4) >= 2) {
-        float v[32];
-        tmem_ld32(tmem + lane_base + kDwCol + f0, v);
         const int row = (warp % 4) * 32 + lane - 64;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) xch[row * TcBwdSmem::kXchStride + f0 + c] = v[c];
+        for (int c = 0; c < NC; ++c) {
+          float v[8];
+          tmem_ld8(tmem + lane_base + kDwCol + f0 + c * 8, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xch[row * TcBwdSmem::kXchStride + f0 + c * 8 + e] = v[e];
+        }
       }
       __syncthreads();
       if ((warp % 4) < 2) {
-        float v[32];
-        tmem_ld32(tmem + lane_base + kDwCol + f0, v);
         const int row = (warp % 4) * 32 + lane;
-        float* dst = part + op.w_off + row * kTcW + f0;
+        float* __restrict__ dst = part + op.w_off + row * kTcW + f0;
+        // all loads first: a load->add->store chain per element would expose one L2 round trip each
+        float cur[kFpt], add[kFpt];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) dst[c] += v[c] + xch[row * TcBwdSmem::kXchStride + f0 + c];
+        for (int e = 0; e < kFpt; ++e) cur[e] = __ldcg(dst + e);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float v[8];
+          tmem_ld8(tmem + lane_base + kDwCol + f0 + c * 8, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) add[c * 8 + e] = v[e] + xch[row * TcBwdSmem::kXchStride + f0 + c * 8 + e];
+        }
+#pragma unroll
+        for (int e = 0; e < kFpt; ++e) __stcg(dst + e, cur[e] + add[e]);
       }
       if (t < 64) part[op.b_off + t] += red_s[t * 8 + 0];
       tc_fence_before_sync();
@@ -852,11 +902,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     // =========================== op 0 (d -> 64), FMA pipe ===========================
     {
       const DevOp& op = prog.ops[0];
-      const float* z0p = stash + (int64_t)op.stash_plane * n_pad + pt;
+      const float* z0p = tstash + op.stash_plane * 128;
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
       __syncthreads();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NC; ++c) {
         float ab0[8], zb0[8];
         tmem_ld8(tmem + lane_base + f0 + c * 8, ab0);
         float s1[8], s2[8], s3[8];
@@ -864,7 +914,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         for (int e = 0; e < 8; ++e) {
           const int f = f0 + c * 8 + e;
           float s0;
-          act_from_basis<(ORDER >= 2)>(op.act, __ldg(z0p + (int64_t)f * n_pad), cache[f * 128 + p],
+          act_from_basis<(ORDER >= 2)>(op.act, __ldg(z0p + f * 128), cache[f * 128 + p],
                                        cache[(64 + f) * 128 + p], s0, s1[e], s2[e], s3[e]);
           zb0[e] = ab0[e] * s1[e];
         }
@@ -877,11 +927,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
-              const float zi = __ldg(z0p + (int64_t)((1 + i) * kTcW + f) * n_pad);
+              const float zi = __ldg(z0p + ((1 + i) * kTcW + f) * 128);
               float zbi = abi[e] * s1[e];
               zb0[e] = fmaf(abi[e] * s2[e], zi, zb0[e]);
               if (ORDER == 2) {
-                const float zii = __ldg(z0p + (int64_t)((1 + D + i) * kTcW + f) * n_pad);
+                const float zii = __ldg(z0p + ((1 + D + i) * kTcW + f) * 128);
                 zbi = fmaf(2.0f * abii[e] * s2[e], zi, zbi);
                 zb0[e] = fmaf(abii[e], fmaf(s3[e] * zi, zi, s2[e] * zii), zb0[e]);
               }

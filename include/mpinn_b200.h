@@ -86,6 +86,11 @@ int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* param
  * jet kernels use.  Exists so the tensor-core conventions can be pinned in isolation by tests. */
 int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream);
 
+/* Diagnostic: when the library is built with -DMPINN_TC_TIMING=1 the tcgen05 reverse kernel accumulates
+ * clock64() deltas per code segment (CTA 0, threads 0 and 224: 2 x 16 counters); this synchronises the
+ * device, copies up to 32 counters to out_host and clears them.  All zeros in a normal build. */
+int mpinn_debug_counters(long long* out_host, int n);
+
 /* sum_i r[i*stride]^2 added into *accum (device scalar).
  * Replaces `torch.sum(r**2)` (reference PINN/PINN.py:59,95,123). */
 int mpinn_sumsq(const float* r, int64_t n, int64_t stride, float* accum, void* stream);

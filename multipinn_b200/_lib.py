@@ -34,6 +34,7 @@ SIGNATURES = {
                                    c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_size_t, c_int, c_void_p]),
     "mpinn_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpinn_debug_counters": (c_int, [c_void_p, c_int]),
     "mpinn_sumsq": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mpinn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float,
                                 c_float, c_float, c_float, c_float, c_void_p]),

@@ -29,6 +29,7 @@ static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m 
 int64_t tc_block_floats(int width);
 cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* packed,
                            cudaStream_t stream);
+cudaError_t read_tc_debug(long long* out, int n);
 
 // Translate the host program into the device description: padded dims, packed-buffer offsets,
 // stash planes.  Returns an error string or nullptr.
@@ -308,6 +309,13 @@ int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void
   if (mode < 0 || mode > 3) return fail("mode must be 0..3");
   cudaError_t e = launch_umma_selftest(mode, a, b, c, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("selftest_umma", e);
+  return 0;
+}
+
+int mpinn_debug_counters(long long* out_host, int n) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = read_tc_debug(out_host, n);
+  if (e != cudaSuccess) return fail_cuda("debug_counters", e);
   return 0;
 }
 

@@ -92,18 +92,22 @@ cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* pack
 // Z[128 x 64] (+)= A[128 x 64] * B[64 x 64]^T, 3xTF32, A/B K-major tiles (hi kb0, hi kb1, lo kb0, lo kb1)
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_tf32(128, 64, 0, 0);
+  // descriptors differ only in their 14-bit start-address field (units of 16 bytes): build them once
+  // and add compile-time constants, so the single issuing thread spends ~3 instructions per MMA
+  const uint64_t a0 = make_desc_sw128(a_tile, 16, 1024);
+  const uint64_t b0 = make_desc_sw128(b_tile, 16, 1024);
   uint32_t acc = 0;
   // the two small correction products go first: the tensor core truncates when it adds into the
   // accumulator, so the large hi*hi partial sums should be the last (and fewest) things added
 #pragma unroll
   for (int prod = 0; prod < 3; ++prod) {
-    const uint32_t a_base = a_tile + (prod == 0 ? 2 * kRegionBytes : 0);    // A_lo * W_hi first
-    const uint32_t b_base = b_tile + (prod == 1 ? 2 * kWRegionBytes : 0);   // then A_hi * W_lo, then hi*hi
+    const uint32_t a_base = (prod == 0 ? 2 * kRegionBytes : 0);    // A_lo * W_hi first
+    const uint32_t b_base = (prod == 1 ? 2 * kWRegionBytes : 0);   // then A_hi * W_lo, then hi*hi
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      const uint32_t a_addr = a_base + (ks >> 2) * kRegionBytes + (ks & 3) * 32;
-      const uint32_t b_addr = b_base + (ks >> 2) * kWRegionBytes + (ks & 3) * 32;
-      mma_tf32_ss(d_tmem, make_desc_sw128(a_addr, 16, 1024), make_desc_sw128(b_addr, 16, 1024), idesc, acc);
+      const uint32_t a_off = a_base + (ks >> 2) * kRegionBytes + (ks & 3) * 32;
+      const uint32_t b_off = b_base + (ks >> 2) * kWRegionBytes + (ks & 3) * 32;
+      mma_tf32_ss(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -150,14 +154,15 @@ __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_
   // (a piece, b piece): weights 2^-16 first, then 2^-8, then the leading product
   constexpr int pa[6] = {2, 1, 0, 1, 0, 0};
   constexpr int pb[6] = {0, 1, 2, 0, 1, 0};
+  const uint64_t a0 = make_desc_sw128(a_tile, 16, 1024);
+  const uint64_t b0 = make_desc_sw128(b_tile, 16, 1024);
   uint32_t acc = 0;
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {   // K = 16 bf16 = 32 bytes per MMA
-      const uint32_t a_addr = a_tile + pa[q] * kBfRegion + ks * 32;
-      const uint32_t b_addr = b_tile + pb[q] * kBfWRegion + ks * 32;
-      mma_bf16_ss(d_tmem, make_desc_sw128(a_addr, 16, 1024), make_desc_sw128(b_addr, 16, 1024), idesc, acc);
+      mma_bf16_ss(d_tmem, a0 + ((pa[q] * kBfRegion + ks * 32) >> 4), b0 + ((pb[q] * kBfWRegion + ks * 32) >> 4),
+                  idesc, acc);
       acc = 1;
     }
   }
@@ -173,15 +178,16 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
   constexpr int zr[4] = {2, 0, 0, 0};
   constexpr int zs[4] = {1, 2, 1, 1};
   constexpr int hp[4] = {0, 2, 1, 0};
+  const uint64_t z1 = make_desc_sw128(z_tile, 1 * kBfRegion, 1024);   // M halves one region apart
+  const uint64_t z2 = make_desc_sw128(z_tile, 2 * kBfRegion, 1024);   // M halves two regions apart
+  const uint64_t h0 = make_desc_sw128(h_tile, kBfRegion, 1024);
   uint32_t acc = accumulate_first;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {   // K = 16 points = two 8-row swizzle atoms (SBO = 1024)
-      const uint32_t a_addr = z_tile + zr[q] * kBfRegion + ks * 2048;
-      const uint32_t b_addr = h_tile + hp[q] * kBfRegion + ks * 2048;
-      mma_bf16_ss(d_tmem, make_desc_sw128(a_addr, zs[q] * kBfRegion, 1024),
-                  make_desc_sw128(b_addr, kBfRegion, 1024), idesc, acc);
+      const uint64_t zd = (zs[q] == 1 ? z1 : z2) + ((zr[q] * kBfRegion + ks * 2048) >> 4);
+      mma_bf16_ss(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -525,6 +531,36 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 }
 
 // ---------------------------------------------------------------------------------------------
+// optional cycle accounting of the reverse kernel (build with -DMPINN_TC_TIMING=1): CTA 0, threads 0
+// and 224 accumulate clock64() deltas per code segment; read back with mpinn_debug_counters().
+// ---------------------------------------------------------------------------------------------
+#ifndef MPINN_TC_TIMING
+#define MPINN_TC_TIMING 0
+#endif
+__device__ long long g_tc_dbg[2][16];
+#if MPINN_TC_TIMING
+#define TC_TIME(slot)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == 0 && (t == 0 || t == 224)) {                      \
+      const long long now_ = clock64();                                 \
+      g_tc_dbg[t == 0 ? 0 : 1][slot] += now_ - dbg_last;                \
+      dbg_last = now_;                                                  \
+    }                                                                   \
+  } while (0)
+#else
+#define TC_TIME(slot) do {} while (0)
+#endif
+
+cudaError_t read_tc_debug(long long* out, int n) {
+  long long h[32];
+  cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+  long long z[32] = {0};
+  return cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
+}
+
+// ---------------------------------------------------------------------------------------------
 // reverse
 // ---------------------------------------------------------------------------------------------
 // Per 128-point tile, walking the layers backwards.  For hidden layer l (64 -> 64) and jet channel j:
@@ -542,13 +578,53 @@ struct TcBwdSmem {
   static constexpr int kW = kH + 3 * kBfRegion;              // W^T operand, 3 pieces        24 KiB
   static constexpr int kCache = kW + kBfWTile;               // basis values [2][64][128]    64 KiB
   static constexpr int kRed = kCache + 2 * 64 * 128 * 4;     // [64][8] reduction scratch      2 KiB
-  static constexpr int kTotal = kRed + 64 * 8 * 4 + 1024;
+  static constexpr int kTotal = kRed + 64 * 8 * 4 + 16 * 16 * 4 + 1024;
   static constexpr int kXchStride = 65;                      // dW half exchange aliases the a tile
 };
 
 // one thread asks the L2 to fetch `bytes` (multiple of 16) starting at p
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Sum each of 16 per-thread values over the 32 lanes of the warp with 16 shuffles (instead of 80):
+// fold the value array in half at every step while exchanging with the lane 16, 8, 4, 2 away.
+// On return every lane holds the warp total of value index (lane >> 1).
+__device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float keep = up ? v[k + 8] : v[k], send = up ? v[k] : v[k + 8];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float keep = up ? a[k + 4] : a[k], send = up ? a[k] : a[k + 4];
+      b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float keep = up ? b[k + 2] : b[k], send = up ? b[k] : b[k + 2];
+      c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool up = lane & 2;
+  float r = (up ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, up ? c[0] : c[1], 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+// fire-and-forget 16-byte vector reduction (sm_90+): *p[0..3] += v
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -565,6 +641,9 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
            float* __restrict__ part_all, int64_t n_params, int n_tiles) {
   constexpr int J = 1 + ORDER * D;
   constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
+  constexpr uint32_t kT0Col = 320;  // TMEM columns caching the activation value of the layer below (J <= 5)
+  constexpr uint32_t kT3Col = 384;  // TMEM columns caching its third derivative
+  static_assert(J * kTcW <= (int)kT0Col, "tcgen05 reverse kernel supports at most 5 jet channels");
   constexpr int NC = kFpt / 8;      // 8-feature chunks per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -573,6 +652,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   uint8_t* w_tile = smem + TcBwdSmem::kW;
   float* cache = reinterpret_cast<float*>(smem + TcBwdSmem::kCache);  // [2][64][128]
   float* red_s = reinterpret_cast<float*>(smem + TcBwdSmem::kRed);    // [64][8]
+  float* bsum_s = red_s + 64 * 8;                                     // [16 warps][16] bias-gradient partials
   float* xch = reinterpret_cast<float*>(h_tile);                      // [64][65] (only between GEMM groups)
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
@@ -582,12 +662,13 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
   const int f0 = fq * kFpt;
 
-  float* part = part_all + (int64_t)blockIdx.x * n_params;
+  const int64_t slab = (n_params + 3) & ~int64_t(3);   // 16-byte aligned slabs
+  float* part = part_all + (int64_t)blockIdx.x * slab;
   for (int64_t i = t; i < n_params; i += kTcThreads) part[i] = 0.0f;
   for (int i = t; i < kBfRegion / 16; i += kTcThreads)
     reinterpret_cast<float4*>(z_tile + 3 * kBfRegion)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t == 0) {
-    mbar_init(&mma_bar, 1);
+    mbar_init(&mma_bar, 2);   // two issuing threads commit per phase
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -601,22 +682,25 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   const int o = prog.n_out;
   const int n_ops = prog.n_ops;
 
-  // fill the basis cache for (layer op, this thread's point and features)
+  // activation coefficients s0..s3 (value and first three derivatives) of layer `op` at this thread's
+  // (point, features), evaluated once: s1/s2 go to shared memory, s0/s3 to spare TMEM columns
   auto fill_cache = [&](const DevOp& op, const float* tstash) {
     const float* z0p = tstash + op.stash_plane * 128;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      float z[8];
+      float z[8], c0[8], c3[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) z[e] = __ldg(z0p + (f0 + c * 8 + e) * 128);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int f = f0 + c * 8 + e;
-        float P, Q;
-        act_basis(op.act, z[e], P, Q);
-        cache[f * 128 + p] = P;
-        cache[(64 + f) * 128 + p] = Q;
+        float c1, c2;
+        act_coeffs<(ORDER >= 2)>(op.act, z[e], c0[e], c1, c2, c3[e]);
+        cache[f * 128 + p] = c1;
+        cache[(64 + f) * 128 + p] = c2;
       }
+      tmem_st8(tmem + lane_base + kT0Col + f0 + c * 8, c0);
+      tmem_st8(tmem + lane_base + kT3Col + f0 + c * 8, c3);
     }
   };
   // sum a per-thread value over the warp's 32 points and add it to the CTA scratch row f, slot < 8
@@ -625,8 +709,12 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     if (lane == 0) atomicAdd(&red_s[f * 8 + slot], v);
   };
 
+#if MPINN_TC_TIMING
+  long long dbg_last = clock64();
+#endif
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t pt = (int64_t)tile * 128 + p;
+    TC_TIME(15);
     const bool valid = pt < n;
     float xv[D];
 #pragma unroll
@@ -673,32 +761,39 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
       }
       // dW_last[k][f] += sum_pts sum_j dz[j][k] a_j[f] ; db_last[k] += sum_pts dz[0][k]
-#pragma unroll 2
-      for (int ff = 0; ff < kFpt; ++ff) {
-        const int f = f0 + ff;
-        float z[J];
+      float g[4][kFpt];
 #pragma unroll
-        for (int j = 0; j < J; ++j) z[j] = __ldg(zp + (j * kTcW + f) * 128);
-        float s0, s1, s2, s3;
-        act_from_basis<false>(pv.act, z[0], cache[f * 128 + p], cache[(64 + f) * 128 + p], s0, s1, s2, s3);
-        float a[J];
-        a[0] = s0;
-        if (ORDER >= 1) {
+      for (int c = 0; c < NC; ++c) {
+        float t0[8];
+        tmem_ld8(tmem + lane_base + kT0Col + f0 + c * 8, t0);
 #pragma unroll
-          for (int i = 0; i < D; ++i) a[1 + i] = s1 * z[1 + i];
-        }
-        if (ORDER >= 2) {
+        for (int e = 0; e < 8; ++e) {
+          const int f = f0 + c * 8 + e;
+          const float s1 = cache[f * 128 + p], s2 = cache[(64 + f) * 128 + p];
+          float a[J];
+          a[0] = t0[e];
+          if (ORDER >= 1) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) a[1 + D + i] = fmaf(s2 * z[1 + i], z[1 + i], s1 * z[1 + D + i]);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < o) {
-            float g = 0.0f;
-#pragma unroll
-            for (int j = 0; j < J; ++j) g = fmaf(dz[j][k], a[j], g);
-            reduce_into(g, f, k);
+            for (int i = 0; i < D; ++i) {
+              const float zi = __ldg(zp + ((1 + i) * kTcW + f) * 128);
+              a[1 + i] = s1 * zi;
+              if (ORDER >= 2) a[1 + D + i] = fmaf(s2 * zi, zi, s1 * __ldg(zp + ((1 + D + i) * kTcW + f) * 128));
+            }
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc = fmaf(dz[j][k], a[j], acc);
+            g[k][c * 8 + e] = acc;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < o) {
+          const float tot = warp_sum16(g[k], lane);
+          if ((lane & 1) == 0) atomicAdd(&red_s[(f0 + (lane >> 1)) * 8 + k], tot);
         }
       }
       if (fq == 0) {
@@ -717,6 +812,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       tc_fence_after_sync();
     }
 
+    TC_TIME(0);   // output op
     // =========================== hidden layers, tensor cores ===========================
     for (int l = n_ops - 2; l >= 1; --l) {
       const DevOp& op = prog.ops[l];
@@ -727,20 +823,19 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       float s1[kFpt], s2[kFpt], s3[kFpt], acc0[kFpt];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        float z[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) z[e] = __ldg(zl + (f0 + c * 8 + e) * 128);
+        float v3[8];
+        tmem_ld8(tmem + lane_base + kT3Col + f0 + c * 8, v3);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int ff = c * 8 + e, f = f0 + ff;
-          float s0;
-          act_from_basis<(ORDER >= 2)>(op.act, z[e], cache[f * 128 + p], cache[(64 + f) * 128 + p], s0,
-                                       s1[ff], s2[ff], s3[ff]);
+          s1[ff] = cache[f * 128 + p];
+          s2[ff] = cache[(64 + f) * 128 + p];
+          s3[ff] = v3[e];
           acc0[ff] = 0.0f;
         }
       }
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
-      __syncthreads();                 // everyone has read the layer-l basis
+      __syncthreads();                 // (the caches are thread-private; this orders red_s)
       fill_cache(pv, tstash);          // now the cache holds layer l-1
       {
         const float4* src = reinterpret_cast<const float4*>(
@@ -761,6 +856,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         l2_prefetch_bulk(nt + prog.ops[n_ops - 2].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
         if (n_ops >= 4) l2_prefetch_bulk(nt + prog.ops[n_ops - 3].stash_plane * 128, (uint32_t)(J * kTcW * 128 * 4));
       }
+      TC_TIME(1);   // per-layer setup: coefficients, cache fill, W tile
       uint32_t dw_acc = 0;
       // channel schedule: (d/dx_i, d2/dx_i2) per direction, value channel last
 #pragma unroll 1
@@ -774,12 +870,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         const int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
         const bool two = is_first && ORDER == 2;
 
-        if (pending) {
-          mbar_wait(&mma_bar, bar_phase);
-          bar_phase ^= 1;
-          pending = 0;
-        }
-        tc_fence_after_sync();
+        float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
           const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
@@ -814,31 +905,42 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             }
             if (jet == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) reduce_into(zb[e], f0 + c * 8 + e, 0);   // bias gradient of layer l
+              for (int e = 0; e < 8; ++e) zb0all[c * 8 + e] = zb[e];
             }
             uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) split_bf16x3(zb[2 * e], zb[2 * e + 1], q1[e], q2[e], q3[e]);
+            // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this
+            // phase has touched so far, so only now -- right before overwriting the tiles -- wait for them.
+            if (c == 0) TC_TIME(2);   // loads + zbar math of chunk 0
+            if (c == 0 && pending) {
+              mbar_wait(&mma_bar, bar_phase);
+              bar_phase ^= 1;
+              pending = 0;
+            }
+            if (c == 0) TC_TIME(3);   // waiting for the previous phase's GEMMs
             *reinterpret_cast<uint4*>(z_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
             *reinterpret_cast<uint4*>(z_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
             *reinterpret_cast<uint4*>(z_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
           }
           // ---------------- activation jet channel of layer l-1 ----------------
           {
-            float y0[8], yi[8], yii[8], av[8];
+            float yi[8], yii[8], av[8];
+            if (jet == 0) {
+              tmem_ld8(tmem + lane_base + kT0Col + f0 + c * 8, av);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int f = f0 + c * 8 + e;
-              y0[e] = __ldg(zm + f * 128);
-              yi[e] = (jet != 0) ? __ldg(zm + ((1 + dir) * kTcW + f) * 128) : 0.0f;
-              yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
-            }
+              for (int e = 0; e < 8; ++e) {
+                const int f = f0 + c * 8 + e;
+                yi[e] = __ldg(zm + ((1 + dir) * kTcW + f) * 128);
+                yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
+              }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int f = f0 + c * 8 + e;
-              float t0, t1, t2, t3;
-              act_from_basis<false>(pv.act, y0[e], cache[f * 128 + p], cache[(64 + f) * 128 + p], t0, t1, t2, t3);
-              av[e] = (jet == 0) ? t0 : (is_first ? t1 * yi[e] : fmaf(t2 * yi[e], yi[e], t1 * yii[e]));
+              for (int e = 0; e < 8; ++e) {
+                const int f = f0 + c * 8 + e;
+                const float t1 = cache[f * 128 + p];
+                av[e] = is_first ? t1 * yi[e] : fmaf(cache[(64 + f) * 128 + p] * yi[e], yi[e], t1 * yii[e]);
+              }
             }
             uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
@@ -848,55 +950,62 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             *reinterpret_cast<uint4*>(h_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
           }
         }
+        if (jet == 0) {
+          static_assert(kFpt == 16, "warp_sum16 reduces exactly 16 features per thread");
+          const float tot = warp_sum16(zb0all, lane);
+          if ((lane & 1) == 0) bsum_s[warp * 16 + (lane >> 1)] = tot;
+        }
+        TC_TIME(4);     // rest of the phase's staging
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        TC_TIME(5);     // phase barrier
+        if (t == 0) {            // one lane of warp 0 issues the input-gradient GEMM ...
           tc_fence_after_sync();
           issue_bf16x3_kmajor(tmem + jet * kTcW, smem_u32(z_tile), smem_u32(w_tile));
+          mma_commit(&mma_bar);
+        } else if (t == 32) {    // ... one lane of warp 1 the weight-gradient GEMM (independent accumulators)
+          tc_fence_after_sync();
           issue_bf16x3_mnmajor(tmem + kDwCol, smem_u32(z_tile), smem_u32(h_tile), dw_acc);
           mma_commit(&mma_bar);
         }
+        TC_TIME(6);     // MMA issue (thread 0 only)
         dw_acc = 1;
         pending = 1;
       }
       mbar_wait(&mma_bar, bar_phase);
+      TC_TIME(7);       // final GEMM wait of the layer
       bar_phase ^= 1;
       pending = 0;
       tc_fence_after_sync();
-      // ---- flush this (tile, layer)'s dW: rows 64..127 of the accumulator fold onto rows 0..63
-      if ((warp % 4) >= 2) {
-        const int row = (warp % 4) * 32 + lane - 64;
+      // ---- flush this (tile, layer)'s dW into the CTA's private slab with fire-and-forget reductions
+      // (no round trip is exposed); accumulator rows r and r+64 both belong to output feature r % 64
+      {
+        const int row = ((warp % 4) * 32 + lane) & 63;
+        float* dst = part + op.w_off + row * kTcW + f0;
+        const bool vec_ok = ((op.w_off & 3) == 0);   // slabs are 16-byte aligned (see launch_bwd_tc)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           float v[8];
           tmem_ld8(tmem + lane_base + kDwCol + f0 + c * 8, v);
+          if (vec_ok) {
+            red_add_v4(dst + c * 8, v[0], v[1], v[2], v[3]);
+            red_add_v4(dst + c * 8 + 4, v[4], v[5], v[6], v[7]);
+          } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) xch[row * TcBwdSmem::kXchStride + f0 + c * 8 + e] = v[e];
+            for (int e = 0; e < 8; ++e) atomicAdd(dst + c * 8 + e, v[e]);
+          }
         }
       }
-      __syncthreads();
-      if ((warp % 4) < 2) {
-        const int row = (warp % 4) * 32 + lane;
-        float* __restrict__ dst = part + op.w_off + row * kTcW + f0;
-        // all loads first: a load->add->store chain per element would expose one L2 round trip each
-        float cur[kFpt], add[kFpt];
-#pragma unroll
-        for (int e = 0; e < kFpt; ++e) cur[e] = __ldcg(dst + e);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          float v[8];
-          tmem_ld8(tmem + lane_base + kDwCol + f0 + c * 8, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) add[c * 8 + e] = v[e] + xch[row * TcBwdSmem::kXchStride + f0 + c * 8 + e];
-        }
-#pragma unroll
-        for (int e = 0; e < kFpt; ++e) __stcg(dst + e, cur[e] + add[e]);
+      if (t < 64) {   // feature t was summed by the 4 warps owning feature quarter t/16
+        const int q = t / kFpt, k = t % kFpt;
+        part[op.b_off + t] += bsum_s[(q * 4 + 0) * 16 + k] + bsum_s[(q * 4 + 1) * 16 + k] +
+                              bsum_s[(q * 4 + 2) * 16 + k] + bsum_s[(q * 4 + 3) * 16 + k];
       }
-      if (t < 64) part[op.b_off + t] += red_s[t * 8 + 0];
       tc_fence_before_sync();
       __syncthreads();
       tc_fence_after_sync();
+      TC_TIME(8);       // dW flush
     }
 
     // =========================== op 0 (d -> 64), FMA pipe ===========================
@@ -905,52 +1014,61 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const float* z0p = tstash + op.stash_plane * 128;
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
       __syncthreads();
+      float zb0[kFpt], zbd[D > 0 ? D : 1][kFpt];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        float ab0[8], zb0[8];
+        float ab0[8];
         tmem_ld8(tmem + lane_base + f0 + c * 8, ab0);
         float s1[8], s2[8], s3[8];
+        tmem_ld8(tmem + lane_base + kT3Col + f0 + c * 8, s3);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int f = f0 + c * 8 + e;
-          float s0;
-          act_from_basis<(ORDER >= 2)>(op.act, __ldg(z0p + f * 128), cache[f * 128 + p],
-                                       cache[(64 + f) * 128 + p], s0, s1[e], s2[e], s3[e]);
-          zb0[e] = ab0[e] * s1[e];
+          s1[e] = cache[f * 128 + p];
+          s2[e] = cache[(64 + f) * 128 + p];
+          zb0[c * 8 + e] = ab0[e] * s1[e];
         }
-        if (ORDER >= 1) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            float abi[8], abii[8];
-            tmem_ld8(tmem + lane_base + (1 + i) * kTcW + f0 + c * 8, abi);
-            if (ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + i) * kTcW + f0 + c * 8, abii);
+        for (int i = 0; i < D; ++i) {
+          float abi[8], abii[8];
+          if (ORDER >= 1) tmem_ld8(tmem + lane_base + (1 + i) * kTcW + f0 + c * 8, abi);
+          if (ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + i) * kTcW + f0 + c * 8, abii);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int f = f0 + c * 8 + e;
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            float zbi = 0.0f;
+            if (ORDER >= 1) {
               const float zi = __ldg(z0p + ((1 + i) * kTcW + f) * 128);
-              float zbi = abi[e] * s1[e];
-              zb0[e] = fmaf(abi[e] * s2[e], zi, zb0[e]);
+              zbi = abi[e] * s1[e];
+              zb0[c * 8 + e] = fmaf(abi[e] * s2[e], zi, zb0[c * 8 + e]);
               if (ORDER == 2) {
                 const float zii = __ldg(z0p + ((1 + D + i) * kTcW + f) * 128);
                 zbi = fmaf(2.0f * abii[e] * s2[e], zi, zbi);
-                zb0[e] = fmaf(abii[e], fmaf(s3[e] * zi, zi, s2[e] * zii), zb0[e]);
+                zb0[c * 8 + e] = fmaf(abii[e], fmaf(s3[e] * zi, zi, s2[e] * zii), zb0[c * 8 + e]);
               }
-              reduce_into(zbi, f, 1 + i);     // d z_i / d W[f][i] = 1
             }
+            zbd[i][c * 8 + e] = zbi;          // d z_i / d W[f][i] = 1
           }
         }
+      }
+      {
+        const int fr = f0 + (lane >> 1);
+        const bool w = (lane & 1) == 0;
+        float tot = warp_sum16(zb0, lane);    // bias
+        if (w) atomicAdd(&red_s[fr * 8 + 0], tot);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int f = f0 + c * 8 + e;
-          reduce_into(zb0[e], f, 0);          // bias
+        for (int i = 0; i < D; ++i) {
+          float tmp[kFpt];
 #pragma unroll
-          for (int i = 0; i < D; ++i) reduce_into(zb0[e] * xv[i], f, 4 + i);
+          for (int e = 0; e < kFpt; ++e) tmp[e] = fmaf(zb0[e], xv[i], zbd[i][e]);   // dL/dW[f][i]
+          tot = warp_sum16(tmp, lane);
+          if (w) atomicAdd(&red_s[fr * 8 + 4 + i], tot);
         }
       }
       __syncthreads();
       for (int i = t; i < 64 * D; i += kTcThreads) {
         const int f = i / D, k = i % D;
-        part[op.w_off + f * D + k] += red_s[f * 8 + 4 + k] + (ORDER >= 1 ? red_s[f * 8 + 1 + k] : 0.0f);
+        part[op.w_off + f * D + k] += red_s[f * 8 + 4 + k];
       }
       if (t < 64) part[op.b_off + t] += red_s[t * 8 + 0];
       tc_fence_before_sync();
@@ -958,6 +1076,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       tc_fence_after_sync();
     }
   }
+  TC_TIME(9);           // op 0 of the last tile (+ tail)
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -983,7 +1102,8 @@ bool tc_forward_supported(const DevProg& prog, int d, int order) {
 }
 
 bool tc_backward_supported(const DevProg& prog, int d, int order) {
-  return tc_forward_supported(prog, d, order);
+  // s0 / s3 of the layer below are cached in the 128 TMEM columns that 5 channels leave free
+  return (1 + order * d) <= 5 && tc_forward_supported(prog, d, order);
 }
 
 template <int D, int ORDER>
@@ -1019,7 +1139,8 @@ __global__ void fold_partials_tc(const float* __restrict__ part, int n_slabs, in
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_params) return;
   float s = 0.0f;
-  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * n_params + i];
+  const int64_t slab = (n_params + 3) & ~int64_t(3);
+  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * slab + i];
   dparams[i] += s;
 }
 
@@ -1033,7 +1154,9 @@ static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, con
   if (e != cudaSuccess) return e;
   const int n_tiles = (int)((n + 127) / 128);
   int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  if (grid > max_slabs) grid = max_slabs;
+  if (grid > max_slabs - 1) grid = max_slabs - 1;   // slabs are padded to 16 bytes: keep one in reserve
+  if (grid < 1) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(part) & 15) != 0) return cudaErrorMisalignedAddress;
   kern<<<grid, kTcThreads, TcBwdSmem::kTotal, stream>>>(prog, params, packed, x, n, dout, stash, n_pad, part,
                                                          n_params, n_tiles);
   e = cudaGetLastError();
@@ -1053,7 +1176,7 @@ cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float*
                                    n_params, dparams, sm_count, stream)
   TC_BWD(1, 0); TC_BWD(1, 1); TC_BWD(1, 2);
   TC_BWD(2, 0); TC_BWD(2, 1); TC_BWD(2, 2);
-  TC_BWD(3, 0); TC_BWD(3, 1); TC_BWD(3, 2);
+  TC_BWD(3, 0); TC_BWD(3, 1);
 #undef TC_BWD
   return cudaErrorInvalidValue;
 }

@@ -252,16 +252,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi takes a moment to start sampling: launch it before the warm-up, use its output for the
+    # timed region (it keeps sampling every 100 ms until stopped)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     epoch = 1
     for _ in range(args.warmup):
         step(epoch)
         epoch += 1
 
     # ---------------- timed region: K steps, inputs resident in HBM
-    clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clocks.start()
     engine.CudaBackend.timings = []
     launches0 = engine.CudaBackend.gpu_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -7,9 +7,10 @@
 // TMEM columns [64j, 64j+64).  The activation and its derivatives are evaluated by 256 threads
 // (2 per point, 32 features each) while staging A_j ("prologue"), sigma'/sigma'' living in registers
 // across the channel loop; the MMA for channel j overlaps the staging of channel j+1 (two A buffers,
-// mbarrier hand-off via tcgen05.commit).  Pre-activation jets go to the HBM stash (same planes as
-// the FFMA engine, so the two engines' forward/reverse kernels are interchangeable) and are read
-// back L2-hot by the next layer's prologue.
+// mbarrier hand-off via tcgen05.commit).  TMEM is managed as eight rotating 64-column blocks: while layer
+// l's accumulators are consumed channel by channel (bias, activation jets, hi/lo split, staging), layer
+// l+1's accumulate into blocks already freed, so the whole forward chain stays on chip; pre-activation
+// jets are written once to the tile-blocked HBM stash for the reverse pass.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -23,6 +24,7 @@ using namespace umma;
 constexpr int kTcW = 64;                 // layer width handled by this engine
 constexpr int kTcThreads = 512;          // 16 warps: 4 threads per point, 16 features each
 constexpr int kFpt = kTcW / (kTcThreads / 128);  // features per thread
+constexpr int kTcBlock = kTcThreads;
 constexpr int kTileRows = 128;
 constexpr int kRegionBytes = kTileRows * 128;       // [128 rows x 32 fp32]  = 16 KiB
 constexpr int kATileBytes = 4 * kRegionBytes;       // hi kb0, hi kb1, lo kb0, lo kb1 = 64 KiB
@@ -90,6 +92,7 @@ cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* pack
 // MMA issue helpers (called by one thread)
 // ---------------------------------------------------------------------------------------------
 // Z[128 x 64] (+)= A[128 x 64] * B[64 x 64]^T, 3xTF32, A/B K-major tiles (hi kb0, hi kb1, lo kb0, lo kb1)
+template <bool ELECT = false>
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_tf32(128, 64, 0, 0);
   // descriptors differ only in their 14-bit start-address field (units of 16 bytes): build them once
@@ -107,7 +110,8 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_ti
     for (int ks = 0; ks < 8; ++ks) {
       const uint32_t a_off = a_base + (ks >> 2) * kRegionBytes + (ks & 3) * 32;
       const uint32_t b_off = b_base + (ks >> 2) * kWRegionBytes + (ks & 3) * 32;
-      mma_tf32_ss(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
+      if (ELECT) mma_tf32_ss_elect(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
+      else mma_tf32_ss(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -149,6 +153,7 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 }
 
 // D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major bf16x3 tiles; smallest products first
+template <bool ELECT = false>
 __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
   // (a piece, b piece): weights 2^-16 first, then 2^-8, then the leading product
@@ -161,8 +166,9 @@ __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_
   for (int q = 0; q < 6; ++q) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {   // K = 16 bf16 = 32 bytes per MMA
-      mma_bf16_ss(d_tmem, a0 + ((pa[q] * kBfRegion + ks * 32) >> 4), b0 + ((pb[q] * kBfWRegion + ks * 32) >> 4),
-                  idesc, acc);
+      const uint64_t ad = a0 + ((pa[q] * kBfRegion + ks * 32) >> 4), bd = b0 + ((pb[q] * kBfWRegion + ks * 32) >> 4);
+      if (ELECT) mma_f16_ss_elect(d_tmem, ad, bd, idesc, acc);
+      else mma_bf16_ss(d_tmem, ad, bd, idesc, acc);
       acc = 1;
     }
   }
@@ -171,6 +177,7 @@ __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_
 // D[128 x 64] (+)= stacked(Z)^T * H over the 128 rows (points) of the tiles, MN-major views.
 //   rows 0..63 : Z1^T (H1 + H2 + H3) + Z3^T H1        rows 64..127 : Z2^T (H1 + H2) (+ Z3^T H3, negligible)
 // Z tile regions: [Z1][Z2][Z3][ZERO]; H tile regions: [H1][H2][H3].  The caller adds the two halves.
+template <bool ELECT = false>
 __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
                                                      uint32_t accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
@@ -187,7 +194,8 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {   // K = 16 points = two 8-row swizzle atoms (SBO = 1024)
       const uint64_t zd = (zs[q] == 1 ? z1 : z2) + ((zr[q] * kBfRegion + ks * 2048) >> 4);
-      mma_bf16_ss(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
+      if (ELECT) mma_f16_ss_elect(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
+      else mma_bf16_ss(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -290,6 +298,36 @@ cudaError_t launch_umma_selftest(int mode, const float* A, const float* B, float
 }
 
 // ---------------------------------------------------------------------------------------------
+// optional cycle accounting of the reverse kernel (build with -DMPINN_TC_TIMING=1): CTA 0, threads 0
+// and 224 accumulate clock64() deltas per code segment; read back with mpinn_debug_counters().
+// ---------------------------------------------------------------------------------------------
+#ifndef MPINN_TC_TIMING
+#define MPINN_TC_TIMING 0
+#endif
+__device__ long long g_tc_dbg[2][16];
+#if MPINN_TC_TIMING
+#define TC_TIME(slot)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == 0 && (t == 0 || t == 224)) {                      \
+      const long long now_ = clock64();                                 \
+      g_tc_dbg[t == 0 ? 0 : 1][slot] += now_ - dbg_last;                \
+      dbg_last = now_;                                                  \
+    }                                                                   \
+  } while (0)
+#else
+#define TC_TIME(slot) do {} while (0)
+#endif
+
+cudaError_t read_tc_debug(long long* out, int n) {
+  long long h[32];
+  cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+  long long z[32] = {0};
+  return cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 struct TcSmem {
@@ -320,8 +358,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   const int p = t % 128, fq = t / 128, warp = t / 32;
   const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
   const int f0 = fq * kFpt;                                   // first feature of this thread
-  // byte offset of this thread's first 16-byte chunk inside an operand tile (K block, row, column)
-  const uint32_t tile_kb = (uint32_t)(f0 / 32) * kRegionBytes;
+  const uint32_t tile_kb = (uint32_t)(f0 / 32) * kRegionBytes;  // K block of this thread's features
   const int col0 = f0 % 32;
 
   if (t == 0) {
@@ -337,6 +374,13 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   uint32_t bar_phase0 = 0, bar_phase1 = 0;   // parity of the next completion to wait for, per A buffer
   int pending0 = 0, pending1 = 0;            // an MMA group is in flight on that buffer
   const int o = prog.n_out;
+  const int n_ops = prog.n_ops;
+
+  // TMEM is managed as eight 64-column blocks.  blk[j] = block holding channel j of the layer being
+  // consumed; channel j of the layer being produced goes to a free block.  Every thread tracks the
+  // same (deterministic) bookkeeping.
+  int blk[J], nblk[J];
+  uint32_t free_mask = 0xFFu;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t pt = (int64_t)tile * 128 + p;
@@ -344,102 +388,109 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     float xv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
-    // this tile's block of the stash: [plane][128 points], this thread's point
-    float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;
+    float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;   // [plane][128 points]
 
-    // ---- op 0: LINEAR(d -> 64) on the FMA pipe: z = W x + b, z_i = W[:, i], z_ii = 0  -> stash
-    {
-      const DevOp& op = prog.ops[0];
-      const float* W = params + op.w_off;
-      const float* b = params + op.b_off;
-#pragma unroll 4
-      for (int ff = 0; ff < kFpt; ++ff) {
-        const int f = f0 + ff;
-        float z0 = __ldg(b + f);
-        float w[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          w[i] = __ldg(W + f * D + i);
-          z0 = fmaf(w[i], xv[i], z0);
-        }
-        float* sp = tstash + (op.stash_plane + f) * 128;
-        sp[0] = z0;
-        if (ORDER >= 1) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) sp[(1 + i) * kTcW * 128] = w[i];
-        }
-        if (ORDER >= 2) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) sp[(1 + D + i) * kTcW * 128] = 0.0f;
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- hidden GEMM layers
-    for (int l = 1; l < prog.n_ops - 1; ++l) {
-      const DevOp& op = prog.ops[l];
-      const DevOp& pv = prog.ops[l - 1];
+    // ---- GEMM layers L = 1 .. n_ops-2; the source layer S = L-1 is consumed channel by channel:
+    //      its pre-activation jets come from registers (S = 0: z = W x + b on the FMA pipe) or from
+    //      TMEM (S >= 1), go to the stash for the reverse pass, and become the A operand of layer L.
+    for (int L = 1; L < n_ops - 1; ++L) {
+      const DevOp& op = prog.ops[L];
+      const DevOp& sv = prog.ops[L - 1];
+      const int S = L - 1;
       {
         const float4* src = reinterpret_cast<const float4*>(packed + op.tc_off);
         float4* dst = reinterpret_cast<float4*>(w_buf);
         for (int i = t; i < kWTileBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-        if (t < kTcW) bias_s[t] = __ldg(params + op.b_off + t);
+        if (t < kTcW) bias_s[t] = __ldg(params + sv.b_off + t);
       }
-      // first and second derivative of the previous layer's activation, this thread's features
-      float s1[kFpt], s2[kFpt];
-      const float* zprev = tstash + pv.stash_plane * 128;
+      __syncthreads();
+      float s1[kFpt], s2[kFpt], zi_keep[kFpt];
+      float* zst = tstash + sv.stash_plane * 128;
 #pragma unroll 1
-      for (int j = 0; j < J; ++j) {
-        const int buf = j & 1;
-        if (buf == 0 ? pending0 : pending1) {
-          if (buf == 0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
-          else          { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
-        }
+      for (int idx = 0; idx < J; ++idx) {
+        // production order: value, then (first, second) derivative per direction
+        int j;
+        if (idx == 0) j = 0;
+        else if (ORDER == 2) j = ((idx - 1) & 1) ? 1 + D + ((idx - 1) >> 1) : 1 + ((idx - 1) >> 1);
+        else j = idx;
+        const bool is_first = (j >= 1 && j <= D);
+        const bool is_second = (j > D);
+        const int dir = is_first ? j - 1 : (is_second ? j - 1 - D : 0);
+        const int buf = idx & 1;
         uint8_t* at = a_buf[buf];
-        // which stash planes this channel needs: z_j, and z_i again for a second-derivative channel
-        const int ji = (j > D) ? j - D : j;
 #pragma unroll
-        for (int c = 0; c < kFpt / 8; ++c) {     // 8 features: all loads first, then the math
-          float za[8], zb[8];
+        for (int c = 0; c < kFpt / 8; ++c) {
+          float z[8];
+          if (S == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = f0 + c * 8 + e;
-            za[e] = __ldcg(zprev + (ji * kTcW + f) * 128);
-            zb[e] = (j > D) ? __ldcg(zprev + (j * kTcW + f) * 128) : 0.0f;
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              if (j == 0) {
+                float v = bias_s[f];
+#pragma unroll
+                for (int i = 0; i < D; ++i) v = fmaf(__ldg(params + sv.w_off + f * D + i), xv[i], v);
+                z[e] = v;
+              } else if (is_first) {
+                z[e] = __ldg(params + sv.w_off + f * D + dir);
+              } else {
+                z[e] = 0.0f;
+              }
+            }
+          } else {
+            tmem_ld8(tmem + lane_base + blk[j] * kTcW + f0 + c * 8, z);
+            if (j == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) z[e] += bias_s[f0 + c * 8 + e];
+            }
           }
           float a[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int ff = c * 8 + e;
+            zst[(j * kTcW + f0 + ff) * 128] = z[e];          // stash for the reverse pass
             if (j == 0) {
               float c0, c1, c2, c3;
-              act_coeffs<false>(pv.act, za[e], c0, c1, c2, c3);
+              act_coeffs<false>(sv.act, z[e], c0, c1, c2, c3);
               s1[ff] = c1;
               s2[ff] = c2;
               a[e] = c0;
-            } else if (j <= D) {
-              a[e] = s1[ff] * za[e];
+            } else if (is_first) {
+              zi_keep[ff] = z[e];
+              a[e] = s1[ff] * z[e];
             } else {
-              a[e] = fmaf(s2[ff] * za[e], za[e], s1[ff] * zb[e]);
+              a[e] = fmaf(s2[ff] * zi_keep[ff], zi_keep[ff], s1[ff] * z[e]);
             }
           }
+          float hi[8], lo[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {          // two 16-byte chunks (4 fp32 each) per 8 features
-            float hi4[4], lo4[4];
+          for (int e = 0; e < 8; ++e) split_tf32(a[e], hi[e], lo[e]);
+          if (c == 0) {   // the GEMM issued two channels ago still reads this buffer
+            if (buf == 0 && pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
+            if (buf == 1 && pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
+          }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_tf32(a[h * 4 + e], hi4[e], lo4[e]);
+          for (int h = 0; h < 2; ++h) {
             const uint32_t off = tile_kb + sw128_offset(p, col0 + c * 8 + h * 4);
-            *reinterpret_cast<float4*>(at + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
-            *reinterpret_cast<float4*>(at + 2 * kRegionBytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            *reinterpret_cast<float4*>(at + off) = make_float4(hi[h * 4], hi[h * 4 + 1], hi[h * 4 + 2], hi[h * 4 + 3]);
+            *reinterpret_cast<float4*>(at + 2 * kRegionBytes + off) =
+                make_float4(lo[h * 4], lo[h * 4 + 1], lo[h * 4 + 2], lo[h * 4 + 3]);
           }
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
+        // blocks of the source layer that nobody needs any more
+        if (S >= 1) {
+          if (j == 0) free_mask |= 1u << blk[0];
+          else if (ORDER == 1) free_mask |= 1u << blk[j];
+          else if (is_second) free_mask |= (1u << blk[j]) | (1u << blk[1 + dir]);
+        }
+        const int nb = __ffs(free_mask) - 1;
+        free_mask &= ~(1u << nb);
+        nblk[j] = nb;
         if (t == 0) {
           tc_fence_after_sync();
-          issue_gemm_kmajor(tmem + j * kTcW, smem_u32(at), smem_u32(w_buf));
+          issue_gemm_kmajor(tmem + nb * kTcW, smem_u32(at), smem_u32(w_buf));
           mma_commit(&mma_bar[buf]);
         }
         if (buf == 0) pending0 = 1; else pending1 = 1;
@@ -447,54 +498,50 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
       if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
       tc_fence_after_sync();
-      // epilogue: z = D + b  -> stash (the next layer's prologue, or the output layer, reads it back)
-      float* zout = tstash + op.stash_plane * 128;
-#pragma unroll 1
-      for (int j = 0; j < J; ++j) {
 #pragma unroll
-        for (int c = 0; c < kFpt / 8; ++c) {
-          float v[8];
-          tmem_ld8(tmem + lane_base + j * kTcW + f0 + c * 8, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = f0 + c * 8 + e;
-            float z = v[e];
-            if (j == 0) z += bias_s[f];
-            zout[(j * kTcW + f) * 128] = z;
-          }
-        }
-      }
-      tc_fence_before_sync();
-      __syncthreads();
+      for (int j = 0; j < J; ++j) blk[j] = nblk[j];
     }
 
-    // ---- output op: LINEAR(64 -> o) on the FMA pipe, from the last hidden layer's stash
+    // ---- output op: LINEAR(64 -> o) on the FMA pipe, fed from the last hidden layer's TMEM blocks
     {
-      const DevOp& op = prog.ops[prog.n_ops - 1];
-      const DevOp& pv = prog.ops[prog.n_ops - 2];
+      const DevOp& op = prog.ops[n_ops - 1];
+      const DevOp& sv = prog.ops[n_ops - 2];
       const float* W = params + op.w_off;
-      const float* zprev = tstash + pv.stash_plane * 128;
+      float* zst = tstash + sv.stash_plane * 128;
+      if (t < kTcW) bias_s[t] = __ldg(params + sv.b_off + t);
+      __syncthreads();
       float acc[J][4];
 #pragma unroll
       for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[j][k] = 0.0f;
-#pragma unroll 2
-      for (int ff = 0; ff < kFpt; ++ff) {
-        const int f = f0 + ff;
-        float z[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) z[j] = __ldcg(zprev + (j * kTcW + f) * 128);
-        act_jets<D, ORDER>(pv.act, z);
+      for (int c = 0; c < kFpt / 8; ++c) {
+        float zj[J][8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < o) {
-            const float w = __ldg(W + k * kTcW + f);
+        for (int j = 0; j < J; ++j) tmem_ld8(tmem + lane_base + blk[j] * kTcW + f0 + c * 8, zj[j]);
 #pragma unroll
-            for (int j = 0; j < J; ++j) acc[j][k] = fmaf(w, z[j], acc[j][k]);
+        for (int e = 0; e < 8; ++e) {
+          const int f = f0 + c * 8 + e;
+          float z[J];
+#pragma unroll
+          for (int j = 0; j < J; ++j) z[j] = zj[j][e];
+          z[0] += bias_s[f];
+#pragma unroll
+          for (int j = 0; j < J; ++j) zst[(j * kTcW + f) * 128] = z[j];
+          act_jets<D, ORDER>(sv.act, z);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < o) {
+              const float w = __ldg(W + k * kTcW + f);
+#pragma unroll
+              for (int j = 0; j < J; ++j) acc[j][k] = fmaf(w, z[j], acc[j][k]);
+            }
           }
         }
       }
+#pragma unroll
+      for (int j = 0; j < J; ++j) free_mask |= 1u << blk[j];
       // combine the feature quarters of each point through shared memory, 8 outputs at a time
       for (int base = 0; base < J * o; base += 8) {
         if (fq > 0) {
@@ -523,41 +570,14 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
         __syncthreads();
       }
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------
-// optional cycle accounting of the reverse kernel (build with -DMPINN_TC_TIMING=1): CTA 0, threads 0
-// and 224 accumulate clock64() deltas per code segment; read back with mpinn_debug_counters().
-// ---------------------------------------------------------------------------------------------
-#ifndef MPINN_TC_TIMING
-#define MPINN_TC_TIMING 0
-#endif
-__device__ long long g_tc_dbg[2][16];
-#if MPINN_TC_TIMING
-#define TC_TIME(slot)                                                   \
-  do {                                                                  \
-    if (blockIdx.x == 0 && (t == 0 || t == 224)) {                      \
-      const long long now_ = clock64();                                 \
-      g_tc_dbg[t == 0 ? 0 : 1][slot] += now_ - dbg_last;                \
-      dbg_last = now_;                                                  \
-    }                                                                   \
-  } while (0)
-#else
-#define TC_TIME(slot) do {} while (0)
-#endif
-
-cudaError_t read_tc_debug(long long* out, int n) {
-  long long h[32];
-  cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
-  if (e != cudaSuccess) return e;
-  for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
-  long long z[32] = {0};
-  return cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1115,7 +1135,7 @@ static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, con
   if (e != cudaSuccess) return e;
   const int n_tiles = (int)((n + 127) / 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  kern<<<grid, kTcThreads, TcSmem::kTotal, stream>>>(prog, params, packed, x, n, out, stash, n_pad, n_tiles);
+  kern<<<grid, kTcBlock, TcSmem::kTotal, stream>>>(prog, params, packed, x, n, out, stash, n_pad, n_tiles);
   return cudaGetLastError();
 }
 

@@ -24,3 +24,17 @@ for th, label in ((0, "thread 0 (issuer)"), (1, "thread 224")):
     print(label, "total cycles", tot, " per tile", tot / 8)
     for k, nm in names.items():
         print(f"   {nm:40s} {vals[k]:12d}  {100*vals[k]/max(tot,1):5.1f}%   per tile-layer {vals[k]/8/8:9.0f}")
+
+# ---- forward
+lib.mpinn_debug_counters(buf, 32)
+out, stash = e.forward(x, 2, True)
+lib.mpinn_debug_counters(buf, 32)
+names = {15: "tile start", 10: "layer: W tile load", 11: "channel: source + activation math chunk0", 12: "channel: wait A buffer",
+         13: "channel: rest of staging", 14: "channel: barrier", 6: "channel: MMA issue", 7: "layer: end GEMM wait", 9: "output op"}
+print("FORWARD")
+for th, label in ((0, "thread 0 (issuer)"), (1, "thread 224")):
+    vals = [buf[th * 16 + i] for i in range(16)]
+    tot = sum(vals)
+    print(label, "total cycles", tot, " per tile", tot / 8)
+    for k, nm in names.items():
+        print(f"   {nm:45s} {vals[k]:12d}  {100*vals[k]/max(tot,1):5.1f}%   per tile-layer {vals[k]/8/8:9.0f}")

@@ -330,7 +330,13 @@ def run_ours(args):
             ach = flops / (bwd_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "jet reverse pass, domain condition (order-2 jets)",
                         "achieved": ach, "peak": peak_bf16, "unit": "TFLOP/s", "frac": ach / peak_bf16,
-                        "peak_source": peak_src, "traffic": None,
+                        "peak_source": peak_src,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
+                        # capture of this exact workload (profiles/r1_tc_ncu_summary.txt); null elsewhere
+                        "traffic": (14.138659e9 + 1.208597e9) if (args.workload == "poisson_2D_1C" and
+                                                                   args.engine == "auto" and
+                                                                   n_domain == 1_000_000) else None,
+                        "traffic_unit": "bytes per launch",
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms,
                         "tf32_matmul_peak_measured": tf32_peak,
                         "frac_of_tf32_peak": (ach / tf32_peak) if tf32_peak else None,
@@ -345,7 +351,7 @@ def run_ours(args):
             "metric": "collocation points/sec per full train step", "value": global_points / (ms * 1e-3),
             "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (3xTF32-class accumulate on the tensor path, fp32 FMA otherwise)", "data": "synthetic",
+            "dtype": "f32 (tensor-core products as 3xTF32 / BF16x3 splits, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {kind} {kw}, {n_domain} domain + {len(spec) - 1}x{n_bound} "
                                    f"boundary points per GPU, calc_loss=mean, Adam(1e-3)+ExponentialLR",
                        "engine": args.engine, "points_per_gpu": local_points,

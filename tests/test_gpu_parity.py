@@ -260,6 +260,42 @@ def test_full_size_properties_poisson_1M():
     assert relerr(out[:, idx].cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
 
 
+# ------------------------------------------------------------------------------ tensor-core conventions
+@pytest.mark.parametrize("mode,label", [(0, "3xTF32 K-major"), (2, "BF16x3 K-major"), (3, "BF16x3 MN-major stacked")])
+def test_umma_selftest(cuda_backend, mode, label):
+    """The descriptor / swizzle / instruction-descriptor conventions of the tcgen05 engine, in isolation:
+    one 128x64x64 (or 128x64x128) product through the same issue helpers the jet kernels use."""
+    torch.manual_seed(mode)
+    a = torch.randn(128, 64, device="cuda")
+    b = torch.randn(64 if mode != 3 else 128, 64, device="cuda")
+    c = torch.zeros(128, 64, device="cuda")
+    cuda_backend.selftest_umma(mode, a, b, c)
+    torch.cuda.synchronize()
+    if mode == 3:
+        ref = a.double().t() @ b.double()
+        got = c[:64].double() + c[64:].double()
+    else:
+        ref = a.double() @ b.double().t()
+        got = c.double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    fp32 = float(((a @ b.t() if mode != 3 else a.t() @ b).double() - ref).abs().max() / ref.abs().max())
+    print(f"{label}: rel err {err:.2e} (cuBLAS fp32 {fp32:.2e})")
+    assert err < 1e-6
+
+
+def test_tcgen05_engine_is_used_and_required():
+    """ENGINE_TCGEN05 must run the tensor-core kernels for an eligible program and refuse an ineligible one
+    (no silent fallback to the FMA engine)."""
+    m, _, _ = full_model("poisson_2D_1C", 5, _lib.ENGINE_TCGEN05)
+    x = torch.rand((1000, 2), device="cuda") * 0.5
+    out, stash = m.jet_engine.forward(x, 2, need_stash=True)
+    ref_out, _ = oracle_jets(m, x.cpu().numpy(), 2)
+    assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
+    r, _, _ = full_model("navier_stokes_2D", 5, _lib.ENGINE_TCGEN05)   # ResNet: not covered by tcgen05 yet
+    with pytest.raises(RuntimeError):
+        r.jet_engine.forward(torch.rand((64, 2), device="cuda"), 2, need_stash=True)
+
+
 # ------------------------------------------------------------------------------ small kernels
 def test_adam_kernel_matches_torch_adam(cuda_backend):
     torch.manual_seed(0)

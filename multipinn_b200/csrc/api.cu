@@ -189,6 +189,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // ------------------------------------------------------------------------------------ C ABI
 using namespace mpinn;
 
+// per-CTA scratch for the jets that travel along a skip connection (tcgen05 engine): 148 CTAs x 7 channels
+// x 64 features x 128 points, L2 resident; sits at the end of the stash (forward) / start of the workspace (reverse)
+static const size_t kSkipScratchFloats = (size_t)148 * 7 * 64 * 128;
+
 extern "C" {
 
 int mpinn_abi_version(void) { return MPINN_ABI_VERSION; }
@@ -198,7 +202,8 @@ const char* mpinn_last_error(void) { return g_err.c_str(); }
 size_t mpinn_stash_bytes(const mpinn_op_t* ops, int n_ops, int d, int order, int64_t n_points) {
   DevProg prog;
   if (build_prog(ops, n_ops, d, order, &prog)) return 0;
-  return (size_t)prog.total_planes * (size_t)round_up64(n_points, 128) * sizeof(float);
+  return ((size_t)prog.total_planes * (size_t)round_up64(n_points, 128) + (prog.has_skip ? kSkipScratchFloats : 0)) *
+         sizeof(float);
 }
 
 // one private slab of n_params floats per resident CTA (at most 4 per SM on a 148-SM part)
@@ -207,7 +212,7 @@ static const int kMaxSlabs = 148 * 4;
 size_t mpinn_backward_workspace_bytes(const mpinn_op_t* ops, int n_ops, int64_t n_params) {
   (void)ops;
   (void)n_ops;
-  return (size_t)kMaxSlabs * (size_t)n_params * sizeof(float);
+  return ((size_t)kMaxSlabs * (size_t)n_params + kSkipScratchFloats) * sizeof(float);
 }
 
 size_t mpinn_packed_bytes(const mpinn_op_t* ops, int n_ops) {
@@ -280,6 +285,10 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (n <= 0) return 0;
   if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
   if (dx) return fail("gradient w.r.t. the points (dx) is not implemented");
+  if (workspace_bytes < kSkipScratchFloats * sizeof(float)) return fail("backward workspace too small");
+  float* skip_scratch = (float*)workspace;                       // first part of the workspace
+  workspace = (void*)((float*)workspace + kSkipScratchFloats);   // slabs follow
+  workspace_bytes -= kSkipScratchFloats * sizeof(float);
   int slabs = (int)(workspace_bytes / ((size_t)n_params * sizeof(float)));
   if (slabs < 1) return fail("backward workspace too small");
   if (slabs > kMaxSlabs) slabs = kMaxSlabs;
@@ -290,7 +299,7 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   int rc;
   if (use_tc(prog, d, order, engine, true, &rc)) {
     e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
-                      n_pad, (float*)workspace, slabs, n_params, dparams, dx, info.sm_count,
+                      n_pad, (float*)workspace, slabs, n_params, dparams, dx, skip_scratch, info.sm_count,
                       (cudaStream_t)stream);
   } else {
     if (rc) return rc;

@@ -389,6 +389,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
     float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;   // [plane][128 points]
+    // jets travelling along a skip connection: this CTA's [channel][feature][point] scratch (L2 resident)
+    float* skip_s = stash + (int64_t)prog.total_planes * n_pad + (int64_t)blockIdx.x * (J * kTcW * 128) + p;
 
     // ---- GEMM layers L = 1 .. n_ops-2; the source layer S = L-1 is consumed channel by channel:
     //      its pre-activation jets come from registers (S = 0: z = W x + b on the FMA pipe) or from
@@ -397,6 +399,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const DevOp& op = prog.ops[L];
       const DevOp& sv = prog.ops[L - 1];
       const int S = L - 1;
+      const bool add_skip = (S >= 1) && (sv.flags & MPINN_FLAG_ADD_SKIP);   // z^S includes the block input
+      const bool save_skip = (op.flags & MPINN_FLAG_SAVE_SKIP);            // a^S is a block input
       {
         const float4* src = reinterpret_cast<const float4*>(packed + op.tc_off);
         float4* dst = reinterpret_cast<float4*>(w_buf);
@@ -442,6 +446,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
               for (int e = 0; e < 8; ++e) z[e] += bias_s[f0 + c * 8 + e];
             }
+            if (add_skip) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) z[e] += skip_s[(j * kTcW + f0 + c * 8 + e) * 128];
+            }
           }
           float a[8];
 #pragma unroll
@@ -460,6 +468,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             } else {
               a[e] = fmaf(s2[ff] * zi_keep[ff], zi_keep[ff], s1[ff] * z[e]);
             }
+          }
+          if (save_skip) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) skip_s[(j * kTcW + f0 + c * 8 + e) * 128] = a[e];
           }
           float hi[8], lo[8];
 #pragma unroll
@@ -527,6 +539,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
           for (int j = 0; j < J; ++j) z[j] = zj[j][e];
           z[0] += bias_s[f];
+          if (sv.flags & MPINN_FLAG_ADD_SKIP) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) z[j] += skip_s[(j * kTcW + f) * 128];
+          }
 #pragma unroll
           for (int j = 0; j < J; ++j) zst[(j * kTcW + f) * 128] = z[j];
           act_jets<D, ORDER>(sv.act, z);
@@ -658,7 +674,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ params,
            const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
            const float* __restrict__ dout, const float* __restrict__ stash, int64_t n_pad,
-           float* __restrict__ part_all, int64_t n_params, int n_tiles) {
+           float* __restrict__ part_all, int64_t n_params, float* __restrict__ skipbar_all, int n_tiles) {
   constexpr int J = 1 + ORDER * D;
   constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
   constexpr uint32_t kT0Col = 320;  // TMEM columns caching the activation value of the layer below (J <= 5)
@@ -681,6 +697,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   const int p = t % 128, fq = t / 128, warp = t / 32, lane = t % 32;
   const uint32_t lane_base = (uint32_t)((warp % 4) * 32) << 16;
   const int f0 = fq * kFpt;
+  // gradient travelling back along a skip connection: this CTA's [channel][feature][point] scratch
+  float* sb = skipbar_all + (int64_t)blockIdx.x * (J * kTcW * 128) + p;
 
   const int64_t slab = (n_params + 3) & ~int64_t(3);   // 16-byte aligned slabs
   float* part = part_all + (int64_t)blockIdx.x * slab;
@@ -839,6 +857,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const DevOp& pv = prog.ops[l - 1];
       const float* zl = tstash + op.stash_plane * 128;    // z^l jets
       const float* zm = tstash + pv.stash_plane * 128;    // z^{l-1} jets
+      const bool store_sb = (op.flags & MPINN_FLAG_ADD_SKIP);                  // zbar^l also flows to the block input
+      const bool add_sb = (prog.ops[l + 1].flags & MPINN_FLAG_SAVE_SKIP);      // abar^l gets the skip branch of the block above
       // first three derivatives of layer l's activation for this thread's features, from the cached basis
       float s1[kFpt], s2[kFpt], s3[kFpt], acc0[kFpt];
 #pragma unroll
@@ -899,6 +919,14 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             float ab[8], ab2[8], zi[8], zii[8], zb[8];
             tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
             if (two) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
+            if (add_sb) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int f = f0 + c * 8 + e;
+                ab[e] += sb[(jet * kTcW + f) * 128];
+                if (two) ab2[e] += sb[((1 + D + dir) * kTcW + f) * 128];
+              }
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
@@ -926,6 +954,10 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             if (jet == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) zb0all[c * 8 + e] = zb[e];
+            }
+            if (store_sb) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sb[(jet * kTcW + f0 + c * 8 + e) * 128] = zb[e];
             }
             uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
@@ -1034,11 +1066,16 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const float* z0p = tstash + op.stash_plane * 128;
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
       __syncthreads();
+      const bool add_sb0 = (prog.ops[1].flags & MPINN_FLAG_SAVE_SKIP);
       float zb0[kFpt], zbd[D > 0 ? D : 1][kFpt];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         float ab0[8];
         tmem_ld8(tmem + lane_base + f0 + c * 8, ab0);
+        if (add_sb0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ab0[e] += sb[(f0 + c * 8 + e) * 128];
+        }
         float s1[8], s2[8], s3[8];
         tmem_ld8(tmem + lane_base + kT3Col + f0 + c * 8, s3);
 #pragma unroll
@@ -1053,6 +1090,13 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           float abi[8], abii[8];
           if (ORDER >= 1) tmem_ld8(tmem + lane_base + (1 + i) * kTcW + f0 + c * 8, abi);
           if (ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + i) * kTcW + f0 + c * 8, abii);
+          if (add_sb0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (ORDER >= 1) abi[e] += sb[((1 + i) * kTcW + f0 + c * 8 + e) * 128];
+              if (ORDER == 2) abii[e] += sb[((1 + D + i) * kTcW + f0 + c * 8 + e) * 128];
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int f = f0 + c * 8 + e;
@@ -1114,8 +1158,15 @@ bool tc_forward_supported(const DevProg& prog, int d, int order) {
   if (first.kind != MPINN_OP_LINEAR || first.in_dim != d || first.out_dim != kTcW || first.flags) return false;
   for (int l = 1; l < prog.n_ops - 1; ++l) {
     const DevOp& op = prog.ops[l];
-    if (op.kind != MPINN_OP_LINEAR || op.in_dim != kTcW || op.out_dim != kTcW || op.flags || op.tc_off < 0)
+    if (op.kind != MPINN_OP_LINEAR || op.in_dim != kTcW || op.out_dim != kTcW || op.tc_off < 0) return false;
+    // residual blocks: a SAVE_SKIP layer immediately followed by the ADD_SKIP layer that closes the block
+    if (op.flags == MPINN_FLAG_SAVE_SKIP) {
+      if (l + 1 > prog.n_ops - 2 || prog.ops[l + 1].flags != MPINN_FLAG_ADD_SKIP) return false;
+    } else if (op.flags == MPINN_FLAG_ADD_SKIP) {
+      if (prog.ops[l - 1].flags != MPINN_FLAG_SAVE_SKIP) return false;
+    } else if (op.flags != 0) {
       return false;
+    }
   }
   const DevOp& last = prog.ops[prog.n_ops - 1];
   return last.kind == MPINN_OP_LINEAR && last.in_dim == kTcW && last.act == MPINN_ACT_NONE && !last.flags;
@@ -1134,7 +1185,8 @@ static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, con
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal);
   if (e != cudaSuccess) return e;
   const int n_tiles = (int)((n + 127) / 128);
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  if (grid > 148) grid = 148;   // the skip scratch holds 148 CTA regions
   kern<<<grid, kTcBlock, TcSmem::kTotal, stream>>>(prog, params, packed, x, n, out, stash, n_pad, n_tiles);
   return cudaGetLastError();
 }
@@ -1168,7 +1220,7 @@ template <int D, int ORDER>
 static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, const float* packed,
                                    const float* x, int64_t n, const float* dout, const float* stash,
                                    int64_t n_pad, float* part, int max_slabs, int64_t n_params,
-                                   float* dparams, int sm_count, cudaStream_t stream) {
+                                   float* dparams, float* skip_scratch, int sm_count, cudaStream_t stream) {
   auto kern = jet_bwd_tc<D, ORDER>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdSmem::kTotal);
   if (e != cudaSuccess) return e;
@@ -1177,8 +1229,9 @@ static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, con
   if (grid > max_slabs - 1) grid = max_slabs - 1;   // slabs are padded to 16 bytes: keep one in reserve
   if (grid < 1) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(part) & 15) != 0) return cudaErrorMisalignedAddress;
+  if (grid > 148) grid = 148;   // the skip scratch holds 148 CTA regions
   kern<<<grid, kTcThreads, TcBwdSmem::kTotal, stream>>>(prog, params, packed, x, n, dout, stash, n_pad, part,
-                                                         n_params, n_tiles);
+                                                         n_params, skip_scratch, n_tiles);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   fold_partials_tc<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, dparams);
@@ -1188,12 +1241,12 @@ static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, con
 cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float* packed, const float* x,
                           int64_t n, int d, int order, const float* dout, const float* stash, int64_t n_pad,
                           float* part, int max_slabs, int64_t n_params, float* dparams, float* dx,
-                          int sm_count, cudaStream_t stream) {
+                          float* skip_scratch, int sm_count, cudaStream_t stream) {
   if (dx != nullptr) return cudaErrorNotSupported;
 #define TC_BWD(D_, O_) \
   if (d == D_ && order == O_) \
     return launch_bwd_tc_t<D_, O_>(prog, params, packed, x, n, dout, stash, n_pad, part, max_slabs, \
-                                   n_params, dparams, sm_count, stream)
+                                   n_params, dparams, skip_scratch, sm_count, stream)
   TC_BWD(1, 0); TC_BWD(1, 1); TC_BWD(1, 2);
   TC_BWD(2, 0); TC_BWD(2, 1); TC_BWD(2, 2);
   TC_BWD(3, 0); TC_BWD(3, 1);

@@ -27,7 +27,7 @@ cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float*
 cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float* packed,
                           const float* x, int64_t n, int d, int order, const float* dout,
                           const float* stash, int64_t n_pad, float* part, int max_slabs,
-                          int64_t n_params, float* dparams, float* dx, int sm_count,
+                          int64_t n_params, float* dparams, float* dx, float* skip_scratch, int sm_count,
                           cudaStream_t stream);
 
 }  // namespace mpinn

@@ -291,9 +291,15 @@ def test_tcgen05_engine_is_used_and_required():
     out, stash = m.jet_engine.forward(x, 2, need_stash=True)
     ref_out, _ = oracle_jets(m, x.cpu().numpy(), 2)
     assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
-    r, _, _ = full_model("navier_stokes_2D", 5, _lib.ENGINE_TCGEN05)   # ResNet: not covered by tcgen05 yet
+    r, _, _ = full_model("navier_stokes_3D", 5, _lib.ENGINE_TCGEN05)   # Fourier features: not on tcgen05 yet
     with pytest.raises(RuntimeError):
-        r.jet_engine.forward(torch.rand((64, 2), device="cuda"), 2, need_stash=True)
+        r.jet_engine.forward(torch.rand((64, 3), device="cuda"), 2, need_stash=True)
+    # residual blocks are covered by the tensor-core engine
+    r, _, _ = full_model("navier_stokes_2D", 5, _lib.ENGINE_TCGEN05)
+    xr = torch.rand((777, 2), device="cuda")
+    out, stash = r.jet_engine.forward(xr, 2, need_stash=True)
+    ref_out, _ = oracle_jets(r, xr.cpu().numpy(), 2)
+    assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
 
 
 # ------------------------------------------------------------------------------ small kernels

@@ -62,6 +62,8 @@ static const char* build_prog(const mpinn_op_t* ops, int n_ops, int d, int order
     if (s.kind == MPINN_OP_FOURIER) {
       if (l != 0) return "FOURIER must be the first op";
       if (s.out_dim % 2) return "FOURIER out_dim must be even";
+      o.stash_plane = planes;   // z = xB duplicated for the sin and cos halves (tcgen05 engine only)
+      planes += J * s.out_dim;
     } else if (s.kind == MPINN_OP_LINEAR) {
       if (s.act < 0 || s.act > 2) return "bad activation";
       if ((s.flags & MPINN_FLAG_ADD_SKIP) && s.out_dim != s.in_dim)

@@ -33,6 +33,10 @@ struct DevProg {
   DevOp ops[kMaxOps];
 };
 
+// internal activation code: cos z, i.e. the second half of a Fourier encoding [sin(xB), cos(xB)] seen as a
+// LINEAR(x -> xB) layer followed by an activation (reference neural_network/fourier_features.py:37-40)
+constexpr int kActCos = 3;
+
 constexpr float kGeluC = 1.0f / 1.41421f;             // the reference's literal constant
 constexpr float kGeluC2 = kGeluC * kGeluC;
 constexpr float kInvSqrtPi = 0.5641895835477563f;
@@ -44,7 +48,7 @@ __device__ __forceinline__ void act_basis(int act, float z, float& P, float& Q) 
     const float cz = kGeluC * z;
     P = 0.5f * (1.0f + erff(cz));
     Q = (kGeluC * kInvSqrtPi) * expf(-(cz * cz));
-  } else if (act == MPINN_ACT_SINE) {
+  } else if (act == MPINN_ACT_SINE || act == kActCos) {
     sincosf(z, &P, &Q);
   } else {
     P = 0.0f;
@@ -68,6 +72,11 @@ __device__ __forceinline__ void act_from_basis(int act, float z, float P, float 
     s1 = Q;
     s2 = -P;
     s3 = -Q;
+  } else if (act == kActCos) {
+    s0 = Q;
+    s1 = -P;
+    s2 = -Q;
+    s3 = P;
   } else {
     s0 = z;
     s1 = 1.0f;

@@ -291,15 +291,21 @@ def test_tcgen05_engine_is_used_and_required():
     out, stash = m.jet_engine.forward(x, 2, need_stash=True)
     ref_out, _ = oracle_jets(m, x.cpu().numpy(), 2)
     assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
-    r, _, _ = full_model("navier_stokes_3D", 5, _lib.ENGINE_TCGEN05)   # Fourier features: not on tcgen05 yet
+    r, _, _ = full_model("burgers_1D", 5, _lib.ENGINE_TCGEN05)   # 128-wide layers: not on tcgen05 yet
     with pytest.raises(RuntimeError):
-        r.jet_engine.forward(torch.rand((64, 3), device="cuda"), 2, need_stash=True)
-    # residual blocks are covered by the tensor-core engine
-    r, _, _ = full_model("navier_stokes_2D", 5, _lib.ENGINE_TCGEN05)
-    xr = torch.rand((777, 2), device="cuda")
-    out, stash = r.jet_engine.forward(xr, 2, need_stash=True)
-    ref_out, _ = oracle_jets(r, xr.cpu().numpy(), 2)
-    assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL
+        r.jet_engine.forward(torch.rand((64, 2), device="cuda"), 2, need_stash=True)
+    # residual blocks and Fourier-feature networks are covered by the tensor-core engine
+    for name, dim in (("navier_stokes_2D", 2), ("navier_stokes_3D", 3)):
+        r, _, _ = full_model(name, 5, _lib.ENGINE_TCGEN05)
+        xr = torch.rand((777, dim), device="cuda")
+        rng = np.random.default_rng(1)
+        out, stash = r.jet_engine.forward(xr, 2, need_stash=True)
+        dout_np = rng.standard_normal((777, 1 + 2 * dim, out.shape[2])).astype(np.float32)
+        dflat = r.jet_engine.backward(xr, 2, torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda(),
+                                      stash).cpu().numpy()
+        ref_out, ref_dp = oracle_jets(r, xr.cpu().numpy(), 2, dout_np)
+        assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL, name
+        assert relerr(dflat, ref_dp) < TOL, name
 
 
 # ------------------------------------------------------------------------------ small kernels

@@ -207,6 +207,35 @@ def run_case(mp, name, modname, factory, model_name, kwargs, counts):
     return out
 
 
+def gradient_reg_case(mp):
+    """Reference GradientLosses(alpha=0.9) (regularization/gradient.py:25-59), poisson_2D_1C's shipped default:
+    3 TrainerOneBatch steps from the poisson golden weights/points; lambdas, losses and weights per step."""
+    g = np.load(os.path.join(HERE, "poisson_2D_1C.npz"))
+    mod = importlib.import_module("examples.poisson_2D_1C.problem")
+    conds, din, dout = mod.poisson_2D_1C()
+    model = mp.neural_network.FNN(input_dim=din, output_dim=dout, hidden_layers=[64] * 9)
+    model.load_state_dict({k: torch.tensor(g["w::" + k]) for k in g["state_keys"]})
+    for i, c in enumerate(conds):
+        p = torch.tensor(g[f"pts{i}"]).requires_grad_()
+        c.generator = _FixedGenerator(p)
+        c.points, c.batch_size = p, len(p)
+    pinn = mp.PINN(model=model, conditions=conds)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.regularization.GradientLosses(alpha=0.9)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg,
+                            callbacks_organizer=mp.CallbacksOrganizer([]))
+    out = {"lambdas": [], "totals": [], "losses": []}
+    for e in range(3):
+        tr.current_epoch = e + 1
+        tr._train_epoch()
+        out["lambdas"].append(reg.lambda_regularization.detach().numpy().copy())
+        out["totals"].append(float(tr.total_loss))
+        out["losses"].append(tr.epoch_loss_detailed.numpy().copy())
+    out = {k: np.array(v) for k, v in out.items()}
+    out["params_after3"] = np.concatenate([p.detach().numpy().reshape(-1) for p in model.parameters()])
+    return out
+
+
 def activation_kats(mp):
     """The reference's own known-answer vectors (tests/neural_network/test_activation_function.py:8-59)."""
     from multipinn.neural_network.activation_function import fused_gelu, fused_sin
@@ -219,12 +248,19 @@ def activation_kats(mp):
 def main():
     mp = import_reference()
     np.savez(os.path.join(HERE, "activation_kats.npz"), **activation_kats(mp))
+    only = sys.argv[1:]
     for case in CASES:
+        if only and case[0] not in only:
+            continue
         out = run_case(mp, *case)
         path = os.path.join(HERE, case[0] + ".npz")
         np.savez_compressed(path, **out)
         print(case[0], "total_f32", out["total_f32"], "total_f64", out["total_f64"],
               os.path.getsize(path) // 1024, "KiB")
+    if not only or "gradient_reg" in only:
+        out = gradient_reg_case(mp)
+        np.savez_compressed(os.path.join(HERE, "poisson_gradient_reg.npz"), **out)
+        print("gradient_reg lambdas", out["lambdas"][-1], "totals", out["totals"])
 
 
 if __name__ == "__main__":

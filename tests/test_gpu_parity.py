@@ -175,6 +175,33 @@ def test_product_path_matches_reference_golden(name):
     assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - g["params_after3"]).max() < 1e-5
 
 
+def test_gradient_losses_regularizer_matches_reference():
+    """poisson_2D_1C's shipped `regularization.type: Gradient` (reference regularization/gradient.py:25-59):
+    lambdas, weighted totals and weights after 3 steps vs the reference's own run (tests/golden)."""
+    import os
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", "poisson_gradient_reg.npz"))
+    model = golden_model("poisson_2D_1C", g)
+    spec, din, dout = problems.CONFIGS["poisson_2D_1C"][0](product_ns())
+    conds = []
+    for i, (fn, (lo, hi)) in enumerate(spec):
+        c = mp.Condition(fn, mp.Hypercube(lo, hi))
+        pts = torch.tensor(g[f"pts{i}"]).cuda().requires_grad_()
+        c.generator = types.SimpleNamespace(n_points=len(pts), generate=lambda cond, model, p=pts: p)
+        conds.append(c)
+    pinn = mp.PINN(model, conds)
+    pinn.update_data()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.GradientLosses(alpha=0.9)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    for e in range(3):
+        tr.current_epoch = e + 1
+        tr._train_epoch()
+        assert relerr(reg.lambda_regularization.cpu().numpy(), gr["lambdas"][e]) < 5e-4
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 2e-5
+    assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - gr["params_after3"]).max() < 2e-5
+
+
 # ------------------------------------------------------------------------------ vs autograd on the GPU
 @pytest.mark.parametrize("name", ["poisson_2D_1C", "burgers_1D", "allen_cahn_2D_1C", "navier_stokes_2D",
                                   "navier_stokes_3D", "regression_1D"])

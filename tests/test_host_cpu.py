@@ -282,3 +282,37 @@ def test_inference_under_no_grad_skips_stash(oracle_backend):
         model(torch.zeros(4, 3))      # wrong input dim
     with pytest.raises(TypeError):
         model(pts.double())           # fp32 only
+
+
+def test_gradient_losses_matches_reference(oracle_backend):
+    """GradientLosses(alpha=0.9) -- poisson_2D_1C's shipped regularizer -- follows the reference's lambdas,
+    weighted totals, component losses and weights over 3 steps (reference regularization/gradient.py:25-59),
+    with ONE reverse launch per condition (the reference runs every condition's backward twice)."""
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", "poisson_gradient_reg.npz"))
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.GradientLosses(alpha=0.9)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    for e in range(3):
+        tr.current_epoch = e + 1
+        oracle_backend.calls.clear()
+        tr._train_epoch()
+        assert sum(1 for c in oracle_backend.calls if c[0] == "bwd") == len(conds)
+        assert relerr(reg.lambda_regularization.numpy(), gr["lambdas"][e]) < 2e-4
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 1e-5
+        assert relerr(tr.epoch_loss_detailed.numpy(), gr["losses"][e]) < 1e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
+
+
+def test_constant_losses(oracle_backend):
+    g = load("poisson_2D_1C")
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    pinn.select_batch(0)
+    tr = types.SimpleNamespace(pinn=pinn)
+    lam = [1.0, 2.0, 3.0, 4.0, 5.0]
+    total, losses = mp.ConstantLosses(lam)(tr)
+    assert relerr(losses.detach().numpy(), g["losses_f64"] * np.array(lam)) < 1e-5
+    assert relerr(total.item(), float((g["losses_f64"] * np.array(lam)).sum())) < 1e-5
+    with pytest.raises(Exception):
+        mp.ConstantLosses([1.0])(tr)

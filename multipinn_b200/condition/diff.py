@@ -70,3 +70,17 @@ def num_laplace(model, arg, fns, eps=2**-7):
         step = (frame[i:i + 1, :] * eps).detach()
         total = total + (model(arg - step) - 2 * fns + model(arg + step))
     return total / (eps * eps)
+
+
+def _diff_residual(model, arg, eps=1e-4):
+    """Self-check used by the reference's tests (``condition/diff.py:208-245``): analytic ``grad`` minus a
+    central difference, one ``[N]`` tensor per (output, input) pair, outputs major."""
+    f = model(arg)
+    n_out, n_in = f.shape[1], arg.shape[1]
+    analytic = [grad(f[:, o], arg) for o in range(n_out)]
+    central = []
+    for i in range(n_in):
+        h = torch.zeros(1, n_in, dtype=arg.dtype, device=arg.device)
+        h[0, i] = eps
+        central.append((model(arg + h) - model(arg - h)) / (2 * eps))
+    return [analytic[o][:, i] - central[i][:, o] for o in range(n_out) for i in range(n_in)]

@@ -16,7 +16,7 @@ class Symbols:
     def __init__(self, variables: str, functions: str, mode: str = "grad"):
         self.variables = self._split(variables)
         self.functions = self._split(functions)
-        self._check_names()
+        self.check_names()
         self.input_dim = len(self.variables)
         self.output_dim = len(self.functions)
         self.mode = mode
@@ -25,7 +25,7 @@ class Symbols:
     def _split(text: str) -> List[str]:
         return text.replace(" ", "").rstrip(",").split(",")
 
-    def _check_names(self):
+    def check_names(self):
         names = self.variables + self.functions
         for name in names:
             if not re.fullmatch(r"[a-zA-Z]", name):
@@ -35,6 +35,11 @@ class Symbols:
 
     def parsing(self, output_format: str) -> List[str]:
         symbols = self._split(output_format)
+        self.check_format(symbols)
+        return symbols
+
+    def check_format(self, derivatives: List[str]) -> None:
+        symbols = derivatives
         if symbols == [""]:
             raise ValueError("No reason to call this function with zero symbols")
         for s in symbols:
@@ -42,14 +47,15 @@ class Symbols:
                 if s not in self.variables and s not in self.functions:
                     raise ValueError(f"Symbol '{s}' is not a defined function or variable.")
                 continue
-            if s.count("_") != 1 or s[1] != "_" or len(s) < 3:
+            if s.count("_") != 1 or s[1] != "_":
                 raise ValueError(f"Invalid symbol format: '{s}'. Expected format is 'u_xyz' or 'u' or 'x'.")
             fn, wrt = s.split("_")
+            if not wrt:
+                raise ValueError(f"Invalid symbol format: '{s}'. Variable part cannot be empty.")
             if fn not in self.functions:
                 raise ValueError(f"Invalid symbol format: '{s}'. Function '{fn}' is not defined.")
             if any(c not in self.variables for c in wrt):
                 raise ValueError(f"Invalid symbol format: '{s}'. Variable '{wrt}' contains undefined variables.")
-        return symbols
 
     @staticmethod
     def _tuple(names: List[str]) -> str:

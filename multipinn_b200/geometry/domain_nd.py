@@ -3,8 +3,10 @@
 (``bbox``, ``random_points``).  Geometry/CSG is outside the accelerated path."""
 import numpy as np
 
+from .geometry import Geometry
 
-class Hypercube:
+
+class Hypercube(Geometry):
     def __init__(self, low, high):
         if len(low) != len(high):
             raise ValueError("Dimensions of low and high do not match.")
@@ -12,9 +14,8 @@ class Hypercube:
         self.high = np.array(high, dtype="float32")
         if np.any(self.low > self.high):
             raise ValueError("low > high")
-        self.dim = len(low)
-        self.bbox = (self.low, self.high)
         self.side_length = self.high - self.low
+        super().__init__(len(low), (self.low, self.high), float(np.linalg.norm(self.side_length)))
 
     def random_points(self, n, random="pseudo"):
         if random != "pseudo":

@@ -224,6 +224,14 @@ def _decode(u: torch.Tensor, b: JetBlock):
 def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
     """``grad(u, arg)`` of the reference (condition/diff.py:25-47), served from the jet block."""
     b = _lookup(u)
+    if b is None and u.grad_fn is not None and arg.requires_grad:
+        # Not an output of a fused jet network: a plain torch module (the families outside the accelerated
+        # path keep the reference's stock-autograd behaviour, condition/diff.py:47).  Outputs of a jet network
+        # that were transformed first (u*v, ...) are NOT connected to `arg` in autograd and still raise below.
+        try:
+            return torch.autograd.grad(u, arg, torch.ones_like(u), create_graph=True)[0]
+        except RuntimeError:
+            pass
     if b is None:
         raise UnsupportedDerivative(
             "grad(u, arg): u is not a view of a model output produced by a multipinn_b200 network. "

@@ -19,12 +19,14 @@ class ResNet(JetModule):
         widths = [int(w) for w in hidden_layers]
         counts = [int(c) for c in blocks] if blocks else [1] * len(widths)
         stages = [nn.Sequential(nn.Linear(input_dim, widths[0]), Sine())]
-        for i, width in enumerate(widths):
-            last = i == len(widths) - 1
-            seq = [res_block(GELU(), width) for _ in range(counts[i])]
-            if not last:
-                seq.append(nn.Sequential(nn.Linear(width, widths[i + 1]), GELU()))
+        # As in the reference (:54-70) the intermediate stages pair hidden_layers[:-1] with blocks[:-1], so a
+        # `blocks` list shorter than `hidden_layers` drops the unpaired stages; the last stage always uses
+        # blocks[-1] at hidden_layers[-1]; a stage never has fewer than one block (:102-105).
+        for width, count, nxt in zip(widths[:-1], counts[:-1], widths[1:]):
+            seq = [res_block(GELU(), width) for _ in range(max(count, 1))]
+            seq.append(nn.Sequential(nn.Linear(width, nxt), GELU()))
             stages.append(nn.Sequential(*seq))
+        stages.append(nn.Sequential(*[res_block(GELU(), widths[-1]) for _ in range(max(counts[-1], 1))]))
         stages.append(nn.Linear(widths[-1], output_dim))
         self.layers = nn.ModuleList(stages)
 

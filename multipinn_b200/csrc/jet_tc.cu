@@ -212,7 +212,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   // TMEM is managed as eight 64-column blocks.  blk[j] = block holding channel j of the layer being
   // consumed; channel j of the layer being produced goes to a free block.  Every thread tracks the
   // same (deterministic) bookkeeping.
-  int blk[J], nblk[J];
+  uint32_t blk_p = 0, nblk_p = 0;   // 4 bits per channel (indexed with a run-time channel number)
+#define BLK(j) ((blk_p >> (4 * (j))) & 7u)
   uint32_t free_mask = 0xFFu;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -277,7 +278,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               }
             }
           } else {
-            tmem_ld8(tmem + lane_base + blk[j] * kTcW + f0 + c * 8, z);
+            tmem_ld8(tmem + lane_base + BLK(j) * kTcW + f0 + c * 8, z);
             if (j == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) z[e] += bias_s[f0 + c * 8 + e];
@@ -329,13 +330,13 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         __syncthreads();
         // blocks of the source layer that nobody needs any more
         if (S >= 1) {
-          if (j == 0) free_mask |= 1u << blk[0];
-          else if (ORDER == 1) free_mask |= 1u << blk[j];
-          else if (is_second) free_mask |= (1u << blk[j]) | (1u << blk[1 + dir]);
+          if (j == 0) free_mask |= 1u << BLK(0);
+          else if (ORDER == 1) free_mask |= 1u << BLK(j);
+          else if (is_second) free_mask |= (1u << BLK(j)) | (1u << BLK(1 + dir));
         }
         const int nb = __ffs(free_mask) - 1;
         free_mask &= ~(1u << nb);
-        nblk[j] = nb;
+        nblk_p |= (uint32_t)nb << (4 * j);
         if (t == 0) {
           tc_fence_after_sync();
           issue_gemm_kmajor(tmem + nb * kTcW, smem_u32(at), smem_u32(w_buf));
@@ -346,8 +347,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
       if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
       tc_fence_after_sync();
-#pragma unroll
-      for (int j = 0; j < J; ++j) blk[j] = nblk[j];
+      blk_p = nblk_p;
+      nblk_p = 0;
     }
 
     // ---- output op: LINEAR(64 -> o) on the FMA pipe, fed from the last hidden layer's TMEM blocks
@@ -367,7 +368,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       for (int c = 0; c < kFpt / 8; ++c) {
         float zj[J][8];
 #pragma unroll
-        for (int j = 0; j < J; ++j) tmem_ld8(tmem + lane_base + blk[j] * kTcW + f0 + c * 8, zj[j]);
+        for (int j = 0; j < J; ++j) tmem_ld8(tmem + lane_base + BLK(j) * kTcW + f0 + c * 8, zj[j]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int f = f0 + c * 8 + e;
@@ -393,7 +394,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
       }
 #pragma unroll
-      for (int j = 0; j < J; ++j) free_mask |= 1u << blk[j];
+      for (int j = 0; j < J; ++j) free_mask |= 1u << BLK(j);
       // combine the feature quarters of each point through shared memory, 8 outputs at a time
       for (int base = 0; base < J * o; base += 8) {
         if (fq > 0) {
@@ -430,6 +431,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+#undef BLK
 }
 
 // ---------------------------------------------------------------------------------------------

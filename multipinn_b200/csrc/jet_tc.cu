@@ -70,7 +70,7 @@ cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* pack
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ B, float* __restrict__ C) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* a_tile = smem;                    // 64 KiB
   uint8_t* b_tile = smem + kATileBytes;      // up to 64 KiB
   __shared__ uint64_t bar;
@@ -169,6 +169,18 @@ struct TcSmem {
   static constexpr int kTotal = kRed + 3 * 128 * 8 * 4 + 1024;  // + alignment slack
 };
 
+template <int I>
+struct IC {
+  static constexpr int value = I;
+};
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F& f) {
+  if constexpr (I < N) {
+    f(IC<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 // FEAT selects the program family at compile time so the plain-FNN kernel carries no extra registers:
 //   0 = plain FNN, 1 = residual blocks (SAVE_SKIP/ADD_SKIP), 2 = Fourier-feature first op
 template <int D, int ORDER, int FEAT>
@@ -179,8 +191,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   constexpr int J = 1 + ORDER * D;
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_buf[2] = {smem + TcSmem::kA0, smem + TcSmem::kA1};
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* w_buf = smem + TcSmem::kW;
   float* bias_s = reinterpret_cast<float*>(smem + TcSmem::kBias);
   float* red_s = reinterpret_cast<float*>(smem + TcSmem::kRed);   // [3][128][8]
@@ -246,18 +257,19 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       __syncthreads();
       float s1[kFpt], s2[kFpt], zi_keep[kFpt];
       float* zst = tstash + sv.stash_plane * 128;
-#pragma unroll 1
-      for (int idx = 0; idx < J; ++idx) {
+      // One channel of the source layer.  The channel index is a compile-time constant (the J calls below
+      // are J specialised copies): which of the three activation-jet formulas applies, the TMEM block, the
+      // stash plane and the A buffer are all resolved by the compiler instead of per-element branches.
+      auto channel = [&](auto idx_c) {
+        constexpr int idx = decltype(idx_c)::value;
         // production order: value, then (first, second) derivative per direction
-        int j;
-        if (idx == 0) j = 0;
-        else if (ORDER == 2) j = ((idx - 1) & 1) ? 1 + D + ((idx - 1) >> 1) : 1 + ((idx - 1) >> 1);
-        else j = idx;
-        const bool is_first = (j >= 1 && j <= D);
-        const bool is_second = (j > D);
-        const int dir = is_first ? j - 1 : (is_second ? j - 1 - D : 0);
-        const int buf = idx & 1;
-        uint8_t* at = a_buf[buf];
+        constexpr int j = (idx == 0) ? 0
+                          : (ORDER == 2 ? (((idx - 1) & 1) ? 1 + D + ((idx - 1) >> 1) : 1 + ((idx - 1) >> 1)) : idx);
+        constexpr bool is_first = (j >= 1 && j <= D);
+        constexpr bool is_second = (j > D);
+        constexpr int dir = is_first ? j - 1 : (is_second ? j - 1 - D : 0);
+        constexpr int buf = idx & 1;
+        uint8_t* at = smem + (buf ? TcSmem::kA1 : TcSmem::kA0);
 #pragma unroll
         for (int c = 0; c < kFpt / 8; ++c) {
           float z[8];
@@ -343,7 +355,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           mma_commit(&mma_bar[buf]);
         }
         if (buf == 0) pending0 = 1; else pending1 = 1;
-      }
+      };
+      static_for<0, J>(channel);
       if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
       if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
       tc_fence_after_sync();

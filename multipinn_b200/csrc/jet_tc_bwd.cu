@@ -123,7 +123,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   constexpr bool TCACHE = (J * kTcW <= (int)kT0Col);
   constexpr int NC = kFpt / 8;      // 8-feature chunks per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* z_tile = smem + TcBwdSmem::kZ;
   uint8_t* h_tile = smem + TcBwdSmem::kH;
   uint8_t* w_tile = smem + TcBwdSmem::kW;

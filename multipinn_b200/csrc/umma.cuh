@@ -18,6 +18,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte aligned start of the dynamic shared memory, computed as pointer + offset so that the result
+// provably stays in the shared address space (a pointer -> integer -> pointer round trip turns every later
+// access into a generic LD/ST instead of LDS/STS)
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  const uint32_t a = smem_u32(raw);
+  return raw + (((a + 1023u) & ~1023u) - a);
+}
+
 // ------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

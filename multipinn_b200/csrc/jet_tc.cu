@@ -169,18 +169,6 @@ struct TcSmem {
   static constexpr int kTotal = kRed + 3 * 128 * 8 * 4 + 1024;  // + alignment slack
 };
 
-template <int I>
-struct IC {
-  static constexpr int value = I;
-};
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F& f) {
-  if constexpr (I < N) {
-    f(IC<I>{});
-    static_for<I + 1, N>(f);
-  }
-}
-
 // FEAT selects the program family at compile time so the plain-FNN kernel carries no extra registers:
 //   0 = plain FNN, 1 = residual blocks (SAVE_SKIP/ADD_SKIP), 2 = Fourier-feature first op
 template <int D, int ORDER, int FEAT>

@@ -368,16 +368,16 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       TC_TIME(1);   // per-layer setup: coefficients, cache fill, W tile
       uint32_t dw_acc = 0;
       // channel schedule: (d/dx_i, d2/dx_i2) per direction, value channel last
-#pragma unroll 1
-      for (int step = 0; step < J; ++step) {
-        int jet;
-        if (step == J - 1) jet = 0;
-        else if (ORDER == 2) jet = (step & 1) ? 1 + D + (step >> 1) : 1 + (step >> 1);
-        else jet = 1 + step;
-        const bool is_first = (jet >= 1 && jet <= D);
-        const bool is_second = (jet > D);
-        const int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
-        const bool two = is_first && ORDER == 2;
+      // One phase = one channel.  The phase index is a compile-time constant (J specialised copies), so the
+      // channel kind, TMEM columns and stash planes are resolved by the compiler, not by per-element branches.
+      auto phase = [&](auto step_c) {
+        constexpr int step = decltype(step_c)::value;
+        constexpr int jet = (step == J - 1) ? 0
+                            : (ORDER == 2 ? ((step & 1) ? 1 + D + (step >> 1) : 1 + (step >> 1)) : 1 + step);
+        constexpr bool is_first = (jet >= 1 && jet <= D);
+        constexpr bool is_second = (jet > D);
+        constexpr int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
+        constexpr bool two = is_first && ORDER == 2;
 
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
 #pragma unroll
@@ -506,7 +506,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         TC_TIME(6);     // MMA issue (thread 0 only)
         dw_acc = 1;
         pending = 1;
-      }
+      };
+      static_for<0, J>(phase);
       mbar_wait(&mma_bar, bar_phase);
       TC_TIME(7);       // final GEMM wait of the layer
       bar_phase ^= 1;

@@ -161,6 +161,19 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
   }
 }
 
+// compile-time loop: f(IC<I>{}) for I in [I0, N)
+template <int I>
+struct IC {
+  static constexpr int value = I;
+};
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F& f) {
+  if constexpr (I < N) {
+    f(IC<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 static inline int tc_feat(const DevProg& prog) {
   if (prog.ops[0].kind == MPINN_OP_FOURIER) return 2;
   return prog.has_skip ? 1 : 0;

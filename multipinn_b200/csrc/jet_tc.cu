@@ -163,9 +163,9 @@ cudaError_t launch_umma_selftest(int mode, const float* A, const float* B, float
 struct TcSmem {
   static constexpr int kA0 = 0;
   static constexpr int kA1 = kATileBytes;
-  static constexpr int kW = 2 * kATileBytes;
-  static constexpr int kBias = kW + kWTileBytes;            // 64 floats
-  static constexpr int kRed = kBias + 256;                  // [3 quarters][128 points][8] floats scratch
+  static constexpr int kW = 2 * kATileBytes;                // two weight-operand buffers (next layer prefetched)
+  static constexpr int kBias = kW + 2 * kWTileBytes;        // 2 x 64 floats
+  static constexpr int kRed = kBias + 512;                  // [3 quarters][128 points][8] floats scratch
   static constexpr int kTotal = kRed + 3 * 128 * 8 * 4 + 1024;  // + alignment slack
 };
 
@@ -180,10 +180,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint8_t* w_buf = smem + TcSmem::kW;
   float* bias_s = reinterpret_cast<float*>(smem + TcSmem::kBias);
   float* red_s = reinterpret_cast<float*>(smem + TcSmem::kRed);   // [3][128][8]
   __shared__ uint64_t mma_bar[2];
+  __shared__ uint64_t w_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x;
@@ -196,9 +196,15 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   if (t == 0) {
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
+    mbar_init(&w_bar[0], 1);
+    mbar_init(&w_bar[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  // Weight operands and biases run one stage ahead of their use: the TMA engine copies the next layer's
+  // packed operand image into the other buffer while this layer computes.
+  if (t < kTcW)
+    bias_s[t] = (HAS_FOURIER && prog.ops[0].kind == MPINN_OP_FOURIER) ? 0.0f : __ldg(params + prog.ops[0].b_off + t);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -207,6 +213,16 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   int pending0 = 0, pending1 = 0;            // an MMA group is in flight on that buffer
   const int o = prog.n_out;
   const int n_ops = prog.n_ops;
+  // stage state: bit 0 = bias buffer of the current stage (toggles every stage, output stage included),
+  // bit 1 = weight buffer of the current GEMM layer (toggles every GEMM layer), bits 2-3 = parity of the
+  // next completion of w_bar[0], w_bar[1] (thread 0 only)
+  uint32_t st = 0;
+#define ST_B (st & 1u)
+#define ST_W ((st >> 1) & 1u)
+  if (t == 0 && (int)blockIdx.x < n_tiles) {
+    mbar_arrive_expect_tx(&w_bar[0], kWTileBytes);
+    bulk_copy_g2s(smem + TcSmem::kW, packed + prog.ops[1].tc_off, kWTileBytes, &w_bar[0]);
+  }
 
   // TMEM is managed as eight 64-column blocks.  blk[j] = block holding channel j of the layer being
   // consumed; channel j of the layer being produced goes to a free block.  Every thread tracks the
@@ -234,15 +250,17 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const int S = L - 1;
       const bool add_skip = HAS_SKIP && (S >= 1) && (sv.flags & MPINN_FLAG_ADD_SKIP);   // z^S includes the block input
       const bool save_skip = HAS_SKIP && (op.flags & MPINN_FLAG_SAVE_SKIP);            // a^S is a block input
-      {
-        const float4* src = reinterpret_cast<const float4*>(packed + op.tc_off);
-        float4* dst = reinterpret_cast<float4*>(w_buf);
-        for (int i = t; i < kWTileBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-        if (t < kTcW)
-          bias_s[t] = (HAS_FOURIER && sv.kind == MPINN_OP_FOURIER) ? 0.0f : __ldg(params + sv.b_off + t);
+      if (t == 0) {   // every GEMM that read the other buffer has completed (waited at the end of its layer)
+        const bool more = (L + 1 < n_ops - 1) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const DevOp& nx = prog.ops[(L + 1 < n_ops - 1) ? L + 1 : 1];
+          const int nbuf = ST_W ^ 1;
+          mbar_arrive_expect_tx(&w_bar[nbuf], kWTileBytes);
+          bulk_copy_g2s(smem + TcSmem::kW + nbuf * kWTileBytes, packed + nx.tc_off, kWTileBytes, &w_bar[nbuf]);
+        }
       }
+      if (t < kTcW) bias_s[(ST_B ^ 1) * kTcW + t] = __ldg(params + op.b_off + t);   // read one stage later
       const int act_src = HAS_FOURIER ? act_of(sv, f0) : sv.act;
-      __syncthreads();
       float s1[kFpt], s2[kFpt], zi_keep[kFpt];
       float* zst = tstash + sv.stash_plane * 128;
       // One channel of the source layer.  The channel index is a compile-time constant (the J calls below
@@ -266,7 +284,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
               if (j == 0) {
-                float v = bias_s[f];
+                float v = bias_s[ST_B * kTcW + f];
 #pragma unroll
                 for (int i = 0; i < D; ++i)
                   v = fmaf(HAS_FOURIER ? first_w(sv, params, f, i, D) : __ldg(params + sv.w_off + f * D + i), xv[i], v);
@@ -281,7 +299,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             tmem_ld8(tmem + lane_base + BLK(j) * kTcW + f0 + c * 8, z);
             if (j == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) z[e] += bias_s[f0 + c * 8 + e];
+              for (int e = 0; e < 8; ++e) z[e] += bias_s[ST_B * kTcW + f0 + c * 8 + e];
             }
             if (add_skip) {
 #pragma unroll
@@ -338,8 +356,12 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         free_mask &= ~(1u << nb);
         nblk_p |= (uint32_t)nb << (4 * j);
         if (t == 0) {
+          if (idx == 0) {   // this layer's weight operand has landed
+            mbar_wait(&w_bar[ST_W], (st >> (2 + ST_W)) & 1u);
+            st ^= 4u << ST_W;
+          }
           tc_fence_after_sync();
-          issue_gemm_kmajor(tmem + nb * kTcW, smem_u32(at), smem_u32(w_buf));
+          issue_gemm_kmajor(tmem + nb * kTcW, smem_u32(at), smem_u32(smem + TcSmem::kW + ST_W * kWTileBytes));
           mma_commit(&mma_bar[buf]);
         }
         if (buf == 0) pending0 = 1; else pending1 = 1;
@@ -350,6 +372,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       tc_fence_after_sync();
       blk_p = nblk_p;
       nblk_p = 0;
+      st ^= 3u;
     }
 
     // ---- output op: LINEAR(64 -> o) on the FMA pipe, fed from the last hidden layer's TMEM blocks
@@ -358,8 +381,9 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const DevOp& sv = prog.ops[n_ops - 2];
       const float* W = params + op.w_off;
       float* zst = tstash + sv.stash_plane * 128;
-      if (t < kTcW) bias_s[t] = __ldg(params + sv.b_off + t);
-      __syncthreads();
+      if (t < kTcW)   // first-op bias for this CTA's next tile
+        bias_s[(ST_B ^ 1) * kTcW + t] =
+            (HAS_FOURIER && prog.ops[0].kind == MPINN_OP_FOURIER) ? 0.0f : __ldg(params + prog.ops[0].b_off + t);
       float acc[J][4];
 #pragma unroll
       for (int j = 0; j < J; ++j)
@@ -376,7 +400,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           float z[J];
 #pragma unroll
           for (int j = 0; j < J; ++j) z[j] = zj[j][e];
-          z[0] += bias_s[f];
+          z[0] += bias_s[ST_B * kTcW + f];
           if (HAS_SKIP && (sv.flags & MPINN_FLAG_ADD_SKIP)) {
 #pragma unroll
             for (int j = 0; j < J; ++j) z[j] += skip_s[(j * kTcW + f) * 128];
@@ -427,12 +451,15 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       tc_fence_before_sync();
       __syncthreads();
       tc_fence_after_sync();
+      st ^= 1u;
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 #undef BLK
+#undef ST_B
+#undef ST_W
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -132,6 +132,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   float* bsum_s = red_s + 64 * 8;                                     // [16 warps][16] bias-gradient partials
   float* xch = reinterpret_cast<float*>(h_tile);                      // [64][65] (only between GEMM groups)
   __shared__ uint64_t mma_bar;
+  __shared__ uint64_t w_bar;      // the TMA engine drops each layer's W^T operand image into w_tile
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x;
@@ -148,6 +149,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     reinterpret_cast<float4*>(z_tile + 3 * kBfRegion)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t == 0) {
     mbar_init(&mma_bar, 2);   // two issuing threads commit per phase
+    mbar_init(&w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -160,6 +162,12 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   int pending = 0;
   const int o = prog.n_out;
   const int n_ops = prog.n_ops;
+  // bytes [kWTileBytes, kWTileBytes + kBfWTile) of a layer's packed block are its bf16x3 W^T operand image
+  auto fetch_w = [&](const DevOp& wop) {
+    mbar_arrive_expect_tx(&w_bar, kBfWTile);
+    bulk_copy_g2s(w_tile, reinterpret_cast<const uint8_t*>(packed + wop.tc_off) + kWTileBytes, kBfWTile, &w_bar);
+  };
+  if (t == 0 && (int)blockIdx.x < n_tiles && n_ops >= 3) fetch_w(prog.ops[n_ops - 2]);
 
   // activation coefficients s0..s3 (value and first three derivatives) of layer `op` at this thread's
   // (point, features), evaluated once: s1/s2 go to shared memory, s0/s3 to spare TMEM columns
@@ -346,13 +354,6 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
       __syncthreads();                 // (the caches are thread-private; this orders red_s)
       fill_cache(pv, tstash);          // now the cache holds layer l-1
-      {
-        const float4* src = reinterpret_cast<const float4*>(
-            reinterpret_cast<const uint8_t*>(packed + op.tc_off) + kWTileBytes);
-        float4* dst = reinterpret_cast<float4*>(w_tile);
-        for (int i = t; i < kBfWTile / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-      }
-      __syncthreads();
 
       // the layer below will be needed next (its z as "z^l", and the one under it as "z^{l-1}"):
       // pull that tile-layer block (J*64 planes x 512 B, contiguous) into L2 while this layer computes
@@ -435,7 +436,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             // phase has touched so far, so only now -- right before overwriting the tiles -- wait for them.
             if (c == 0) TC_TIME(2);   // loads + zbar math of chunk 0
             if (c == 0 && pending) {
-              mbar_wait(&mma_bar, bar_phase);
+              mbar_wait(&mma_bar, bar_phase & 1);
               bar_phase ^= 1;
               pending = 0;
             }
@@ -495,6 +496,10 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         __syncthreads();
         TC_TIME(5);     // phase barrier
         if (t == 0) {            // one lane of warp 0 issues the input-gradient GEMM ...
+          if (step == 0) {       // this layer's W^T operand has landed (bit 1 of bar_phase: parity of w_bar)
+            mbar_wait(&w_bar, (bar_phase >> 1) & 1);
+            bar_phase ^= 2;
+          }
           tc_fence_after_sync();
           issue_bf16x3_kmajor(tmem + jet * kTcW, smem_u32(z_tile), smem_u32(w_tile));
           mma_commit(&mma_bar);
@@ -508,11 +513,15 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         pending = 1;
       };
       static_for<0, J>(phase);
-      mbar_wait(&mma_bar, bar_phase);
+      mbar_wait(&mma_bar, bar_phase & 1);
       TC_TIME(7);       // final GEMM wait of the layer
       bar_phase ^= 1;
       pending = 0;
       tc_fence_after_sync();
+      if (t == 0) {     // w_tile is free again: fetch the next layer's (or the next tile's top layer's) operand
+        if (l > 1) fetch_w(prog.ops[l - 1]);
+        else if (tile + (int)gridDim.x < n_tiles) fetch_w(prog.ops[n_ops - 2]);
+      }
       // ---- flush this (tile, layer)'s dW into the CTA's private slab with fire-and-forget reductions
       // (no round trip is exposed); accumulator rows r and r+64 both belong to output feature r % 64
       {

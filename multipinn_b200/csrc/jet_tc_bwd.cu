@@ -384,6 +384,18 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
         for (int c = 0; c < NC; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
           const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
+          // the layer-below jets needed by the second half of this chunk are requested first, so that their
+          // latency overlaps the zbar math (nothing between here and their use can be reordered by the
+          // compiler across the barrier / tensor-memory instructions)
+          float yi[8], yii[8];
+          if (jet != 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int f = f0 + c * 8 + e;
+              yi[e] = __ldg(zm + ((1 + dir) * kTcW + f) * 128);
+              yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
+            }
+          }
           // ---------------- zbar of layer l ----------------
           {
             float ab[8], ab2[8], zi[8], zii[8], zb[8];
@@ -447,7 +459,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
           // ---------------- activation jet channel of layer l-1 ----------------
           {
-            float yi[8], yii[8], av[8];
+            float av[8];
             if (jet == 0 && TCACHE) {
               tmem_ld8(tmem + lane_base + kT0Col + f0 + c * 8, av);
             } else if (jet == 0) {
@@ -457,12 +469,6 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 coeffs_at(pv, tstash, f0 + c * 8 + e, av[e], t1, t2, t3);
               }
             } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int f = f0 + c * 8 + e;
-                yi[e] = __ldg(zm + ((1 + dir) * kTcW + f) * 128);
-                yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
-              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int f = f0 + c * 8 + e;

@@ -328,19 +328,28 @@ def run_ours(args):
         if bwd:
             bwd_ms = sum(bwd) / len(bwd)
             flops = n_domain * J * 4 * Pw
+            hidden = sum(int(r[2]) for r in model.jet_program()[:-1])   # stashed pre-activation features per point
+            stash_bytes = n_domain * J * hidden * 4
+            hbm_peak = peaks.get("hbm_gbs", 6500.0)
             ach = flops / (bwd_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "jet reverse pass, domain condition (order-2 jets)",
                         "achieved": ach, "peak": peak_bf16, "unit": "TFLOP/s", "frac": ach / peak_bf16,
                         "peak_source": peak_src,
                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
                         # capture of this exact workload (profiles/r1_tc_ncu_summary.txt); null elsewhere
-                        "traffic": (14.667502e9 + 1.211538e9) if (args.workload == "poisson_2D_1C" and
+                        "traffic": (14.093616e9 + 1.135286e9) if (args.workload == "poisson_2D_1C" and
                                                                    args.engine == "auto" and
                                                                    n_domain == 1_000_000) else None,
                         "traffic_unit": "bytes per launch",
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms,
                         "tf32_matmul_peak_measured": tf32_peak,
                         "frac_of_tf32_peak": (ach / tf32_peak) if tf32_peak else None,
+                        # memory view of the same two kernels: the pre-activation jet stash is the algorithmic
+                        # HBM traffic (written once by the forward pass, read once by the reverse pass)
+                        "stash_bytes_per_launch": stash_bytes,
+                        "hbm_peak_GBps": hbm_peak,
+                        "hbm_frac_reverse": stash_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak,
+                        "hbm_frac_forward": (stash_bytes / (sum(fwd) / len(fwd) * 1e-3) / 1e9 / hbm_peak) if fwd else None,
                         "fwd_avg_launch_ms": (sum(fwd) / len(fwd)) if fwd else None,
                         "fwd_achieved": (n_domain * J * 2 * Pw / (sum(fwd) / len(fwd) * 1e-3) / 1e12) if fwd else None}
         step_flops = 0

@@ -396,6 +396,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
             }
           }
+          uint32_t zq1[4], zq2[4], zq3[4];   // bf16x3 pieces of this chunk's zbar, stored after the a-channel math
           // ---------------- zbar of layer l ----------------
           {
             float ab[8], ab2[8], zi[8], zii[8], zb[8];
@@ -441,21 +442,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
               for (int e = 0; e < 8; ++e) sb[(jet * kTcW + f0 + c * 8 + e) * 128] = zb[e];
             }
-            uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16x3(zb[2 * e], zb[2 * e + 1], q1[e], q2[e], q3[e]);
-            // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this
-            // phase has touched so far, so only now -- right before overwriting the tiles -- wait for them.
-            if (c == 0) TC_TIME(2);   // loads + zbar math of chunk 0
-            if (c == 0 && pending) {
-              mbar_wait(&mma_bar, bar_phase & 1);
-              bar_phase ^= 1;
-              pending = 0;
-            }
-            if (c == 0) TC_TIME(3);   // waiting for the previous phase's GEMMs
-            *reinterpret_cast<uint4*>(z_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-            *reinterpret_cast<uint4*>(z_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
-            *reinterpret_cast<uint4*>(z_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+            for (int e = 0; e < 4; ++e) split_bf16x3(zb[2 * e], zb[2 * e + 1], zq1[e], zq2[e], zq3[e]);
           }
           // ---------------- activation jet channel of layer l-1 ----------------
           {
@@ -486,6 +474,19 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) split_bf16x3(av[2 * e], av[2 * e + 1], q1[e], q2[e], q3[e]);
+            // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this
+            // phase has touched so far, so only now -- with the first chunk's math of BOTH tiles done and right
+            // before overwriting them -- wait for those GEMMs.
+            if (c == 0) TC_TIME(2);   // loads + math of chunk 0
+            if (c == 0 && pending) {
+              mbar_wait(&mma_bar, bar_phase & 1);
+              bar_phase ^= 1;
+              pending = 0;
+            }
+            if (c == 0) TC_TIME(3);   // waiting for the previous phase's GEMMs
+            *reinterpret_cast<uint4*>(z_tile + off) = make_uint4(zq1[0], zq1[1], zq1[2], zq1[3]);
+            *reinterpret_cast<uint4*>(z_tile + kBfRegion + off) = make_uint4(zq2[0], zq2[1], zq2[2], zq2[3]);
+            *reinterpret_cast<uint4*>(z_tile + 2 * kBfRegion + off) = make_uint4(zq3[0], zq3[1], zq3[2], zq3[3]);
             *reinterpret_cast<uint4*>(h_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
             *reinterpret_cast<uint4*>(h_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
             *reinterpret_cast<uint4*>(h_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);

@@ -283,13 +283,30 @@ def run_ours(args):
     final_loss = float(trainer.total_loss)
 
     # ---------------- e2e: same step through the public API with HOST inputs (pinned) + loss readback
+    # Every step's points come from pinned host memory.  The copy of step k+1's points runs on a second stream
+    # into the other of two device buffers while step k computes (what a training loop fed from the host does);
+    # the step waits on the copy's event before its first kernel, and the losses are read back every step.
+    copy_stream = torch.cuda.Stream()
+    bufs = [[torch.empty_like(p) for p in dev_pts] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(k):
+        with torch.cuda.stream(copy_stream):
+            for i, h in enumerate(host_pts):
+                bufs[k][i].copy_(h, non_blocking=True)
+            ready[k].record(copy_stream)
+
     def e2e_step(epoch):
-        for i, h in enumerate(host_pts):
-            dev_pts[i] = h.to(dev, non_blocking=True).requires_grad_()
+        k = epoch & 1
+        torch.cuda.current_stream().wait_event(ready[k])
+        for i in range(len(host_pts)):
+            dev_pts[i] = bufs[k][i].detach().requires_grad_()
+        prefetch(k ^ 1)   # (the step that last read that buffer has completed: its losses were read back)
         pinn.update_data()
         step(epoch)
         return float(trainer.total_loss), trainer.epoch_loss_detailed.cpu()
 
+    prefetch(epoch & 1)
     e2e_step(epoch)
     epoch += 1
     barrier()

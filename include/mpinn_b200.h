@@ -50,7 +50,8 @@ const char* mpinn_last_error(void);
  * and bytes of workspace the reverse pass needs (per-CTA partial parameter gradients). */
 size_t mpinn_stash_bytes(const mpinn_op_t* ops_host, int n_ops, int d, int order, int64_t n_points);
 size_t mpinn_backward_workspace_bytes(const mpinn_op_t* ops_host, int n_ops, int64_t n_params);
-/* Bytes of the packed-weight buffer (transposed / padded / hi-lo split copies of the weights). */
+/* Bytes of the packed-weight buffer (transposed / padded / hi-lo split copies of the weights).
+ * The buffer must be 16-byte aligned (its operand images are fetched by the TMA engine). */
 size_t mpinn_packed_bytes(const mpinn_op_t* ops_host, int n_ops);
 
 /* Re-pack the flat parameter vector into the kernels' operand layouts.  Call once after every

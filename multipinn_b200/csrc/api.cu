@@ -229,6 +229,7 @@ int mpinn_pack_params(const mpinn_op_t* ops, int n_ops, const float* params, voi
   const char* err = build_prog(ops, n_ops, ops ? ops[0].in_dim : 0, 0, &prog);
   if (err) return fail(err);
   if (!params || !packed) return fail("null pointer");
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail("packed buffer must be 16-byte aligned");
   dim3 grid(16, n_ops);
   pack_params_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prog, params, (float*)packed);
   cudaError_t e = cudaGetLastError();
@@ -258,6 +259,7 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   if (ops[0].in_dim != d) return fail("first op in_dim must equal d");
   if (n <= 0) return 0;
   if (!params || !packed || !x || !out) return fail("null pointer");
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail("packed buffer must be 16-byte aligned");
   DeviceInfo info;
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
@@ -286,6 +288,7 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (err) return fail(err);
   if (n <= 0) return 0;
   if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail("packed buffer must be 16-byte aligned");
   if (dx) return fail("gradient w.r.t. the points (dx) is not implemented");
   if (workspace_bytes < kSkipScratchFloats * sizeof(float)) return fail("backward workspace too small");
   float* skip_scratch = (float*)workspace;                       // first part of the workspace

@@ -125,6 +125,38 @@ def test_ragged_point_counts(n, eng):
     assert relerr(dflat, ref_dp) < TOL
 
 
+@pytest.mark.parametrize("name,dim", [("poisson_2D_1C", 2), ("navier_stokes_2D", 2), ("navier_stokes_3D", 3)])
+def test_persistent_tiles_match_oracle(name, dim):
+    """More tiles than CTAs: every CTA walks several tiles, so the operand prefetch that runs ahead across tile
+    boundaries (next tile's first layer fetched during this tile's last one) is on the path."""
+    m, _, _ = full_model(name, 5, _lib.ENGINE_TCGEN05)
+    n = 148 * 128 * 2 + 77
+    rng = np.random.default_rng(7)
+    x_np = rng.random((n, dim), dtype=np.float32) * 0.5
+    x = torch.tensor(x_np).cuda()
+    for order in (2, 0):
+        out, stash = m.jet_engine.forward(x, order, need_stash=True)
+        dout_np = rng.standard_normal((n, 1 + order * dim, out.shape[2])).astype(np.float32)
+        dflat = m.jet_engine.backward(x, order, torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda(),
+                                      stash).cpu().numpy()
+        ref_out, ref_dp = oracle_jets(m, x_np, order, dout_np)
+        assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref_out) < TOL, (name, order)
+        assert relerr(dflat, ref_dp) < TOL, (name, order)
+
+
+def test_misaligned_packed_buffer_is_rejected(cuda_backend):
+    """The packed operand images are fetched by the TMA engine: the C ABI refuses a buffer that is not 16-byte aligned."""
+    m, _, _ = full_model("poisson_2D_1C")
+    eng = m.jet_engine
+    x = torch.rand((64, 2), device="cuda")
+    eng.forward(x, 0, need_stash=False)   # builds the flat / packed buffers
+    ops = m.jet_program()
+    raw = torch.zeros(cuda_backend.packed_bytes(ops) // 4 + 8, device="cuda")
+    out = torch.empty((1, 64, 1), device="cuda")
+    with pytest.raises(RuntimeError, match="16-byte"):
+        cuda_backend.jet_forward(ops, eng.flat, raw[1:], x, 0, out, None)
+
+
 def test_empty_input_is_a_noop():
     m, _, _ = full_model("poisson_2D_1C")
     x = torch.zeros((0, 2), device="cuda")

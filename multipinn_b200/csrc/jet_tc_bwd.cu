@@ -396,10 +396,17 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
             }
           }
+          float zi[8], zii[8];                // (this layer's jets: requested up front for the same reason)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            zi[e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
+            zii[e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
+          }
           uint32_t zq1[4], zq2[4], zq3[4];   // bf16x3 pieces of this chunk's zbar, stored after the a-channel math
           // ---------------- zbar of layer l ----------------
           {
-            float ab[8], ab2[8], zi[8], zii[8], zb[8];
+            float ab[8], ab2[8], zb[8];
             tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
             if (two) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
             if (add_sb) {
@@ -409,12 +416,6 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 ab[e] += sb[(jet * kTcW + f) * 128];
                 if (two) ab2[e] += sb[((1 + D + dir) * kTcW + f) * 128];
               }
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int f = f0 + c * 8 + e;
-              zi[e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
-              zii[e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {

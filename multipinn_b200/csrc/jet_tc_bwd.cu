@@ -381,6 +381,16 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         constexpr bool two = is_first && ORDER == 2;
 
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
+        float zi_c[NC][8], zii_c[NC][8];
+        auto request_zl = [&](int c) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + c * 8 + e;
+            zi_c[c][e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
+            zii_c[c][e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
+          }
+        };
+        request_zl(0);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {          // 8 features per chunk = one 16-byte bf16 store per piece
           const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
@@ -396,13 +406,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
             }
           }
-          float zi[8], zii[8];                // (this layer's jets: requested up front for the same reason)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = f0 + c * 8 + e;
-            zi[e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
-            zii[e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
-          }
+          float (&zi)[8] = zi_c[c];           // (this layer's jets: requested one chunk ahead, see below)
+          float (&zii)[8] = zii_c[c];
           uint32_t zq1[4], zq2[4], zq3[4];   // bf16x3 pieces of this chunk's zbar, stored after the a-channel math
           // ---------------- zbar of layer l ----------------
           {
@@ -479,6 +484,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             // phase has touched so far, so only now -- with the first chunk's math of BOTH tiles done and right
             // before overwriting them -- wait for those GEMMs.
             if (c == 0) TC_TIME(2);   // loads + math of chunk 0
+            if (c + 1 < NC) request_zl(c + 1);   // in flight across the wait and the stores below
             if (c == 0 && pending) {
               mbar_wait(&mma_bar, bar_phase & 1);
               bar_phase ^= 1;

@@ -382,6 +382,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
         float zi_c[NC][8], zii_c[NC][8];
+        uint32_t zq[NC][3][4], hq[NC][3][4];   // this phase's bf16x3 operand pieces, stored after the GEMM wait
         auto request_zl = [&](int c) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -408,7 +409,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
           float (&zi)[8] = zi_c[c];           // (this layer's jets: requested one chunk ahead, see below)
           float (&zii)[8] = zii_c[c];
-          uint32_t zq1[4], zq2[4], zq3[4];   // bf16x3 pieces of this chunk's zbar, stored after the a-channel math
+          uint32_t (&zq1)[4] = zq[c][0], (&zq2)[4] = zq[c][1], (&zq3)[4] = zq[c][2];   // bf16x3 pieces of zbar
           // ---------------- zbar of layer l ----------------
           {
             float ab[8], ab2[8], zb[8];
@@ -477,26 +478,28 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 av[e] = is_first ? t1 * yi[e] : fmaf(t2 * yi[e], yi[e], t1 * yii[e]);
               }
             }
-            uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16x3(av[2 * e], av[2 * e + 1], q1[e], q2[e], q3[e]);
-            // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this
-            // phase has touched so far, so only now -- with the first chunk's math of BOTH tiles done and right
-            // before overwriting them -- wait for those GEMMs.
-            if (c == 0) TC_TIME(2);   // loads + math of chunk 0
-            if (c + 1 < NC) request_zl(c + 1);   // in flight across the wait and the stores below
-            if (c == 0 && pending) {
-              mbar_wait(&mma_bar, bar_phase & 1);
-              bar_phase ^= 1;
-              pending = 0;
-            }
-            if (c == 0) TC_TIME(3);   // waiting for the previous phase's GEMMs
-            *reinterpret_cast<uint4*>(z_tile + off) = make_uint4(zq1[0], zq1[1], zq1[2], zq1[3]);
-            *reinterpret_cast<uint4*>(z_tile + kBfRegion + off) = make_uint4(zq2[0], zq2[1], zq2[2], zq2[3]);
-            *reinterpret_cast<uint4*>(z_tile + 2 * kBfRegion + off) = make_uint4(zq3[0], zq3[1], zq3[2], zq3[3]);
-            *reinterpret_cast<uint4*>(h_tile + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-            *reinterpret_cast<uint4*>(h_tile + kBfRegion + off) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
-            *reinterpret_cast<uint4*>(h_tile + 2 * kBfRegion + off) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+            for (int e = 0; e < 4; ++e) split_bf16x3(av[2 * e], av[2 * e + 1], hq[c][0][e], hq[c][1][e], hq[c][2][e]);
+            if (c + 1 < NC) request_zl(c + 1);
+          }
+        }
+        // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this phase has
+        // touched, so they are waited for only now -- with all of this phase's math done and its bf16x3 pieces
+        // in registers -- right before the tiles are overwritten.
+        TC_TIME(2);   // loads + math
+        if (pending) {
+          mbar_wait(&mma_bar, bar_phase & 1);
+          bar_phase ^= 1;
+          pending = 0;
+        }
+        TC_TIME(3);   // waiting for the previous phase's GEMMs
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<uint4*>(z_tile + q * kBfRegion + off) = make_uint4(zq[c][q][0], zq[c][q][1], zq[c][q][2], zq[c][q][3]);
+            *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(hq[c][q][0], hq[c][q][1], hq[c][q][2], hq[c][q][3]);
           }
         }
         if (jet == 0) {

@@ -74,7 +74,8 @@ int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params
  * Replaces `loss.backward()` through the double-backward graph (reference trainer/trainer.py:141).
  *   dout    [J,n,o]  gradient w.r.t. the forward's `out`
  *   dparams [P]      ACCUMULATED into (+=); P = number of floats in `params`
- *   dx      [n,d]    written if non-NULL (gradient w.r.t. the points), else skipped          */
+ *   dx      [n,d]    written if non-NULL (gradient w.r.t. the points: the `points.grad` the reference's
+ *                    `batch_loss.backward()` leaves behind), else skipped; refused for a FOURIER first op */
 int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* params,
                        const void* packed, const float* x, int64_t n, int d, int order,
                        const float* dout, const void* stash, float* dparams, int64_t n_params,

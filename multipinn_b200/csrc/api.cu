@@ -289,7 +289,8 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (n <= 0) return 0;
   if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail("packed buffer must be 16-byte aligned");
-  if (dx) return fail("gradient w.r.t. the points (dx) is not implemented");
+  if (dx && ops[0].kind == MPINN_OP_FOURIER)
+    return fail("gradient w.r.t. the points (dx) through a Fourier-feature first op is not implemented");
   if (workspace_bytes < kSkipScratchFloats * sizeof(float)) return fail("backward workspace too small");
   float* skip_scratch = (float*)workspace;                       // first part of the workspace
   workspace = (void*)((float*)workspace + kSkipScratchFloats);   // slabs follow

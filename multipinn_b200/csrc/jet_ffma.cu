@@ -316,6 +316,13 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
         for (int q = 0; q < TP; ++q) s += bufG[f * TPP + q];
         part[op.b_off + f] += s;
       }
+      // gradient w.r.t. the points: x enters only through the value channel of op 0 (z = W x + b), so
+      // dL/dx_i = sum_o W[o][i] zbar_0[o]  (a Fourier first op is refused at the C ABI)
+      if (l == 0 && dx != nullptr && op.kind == MPINN_OP_LINEAR && g < D && pt < n) {
+        float s = 0.0f;
+        for (int oo = 0; oo < op.out_dim; ++oo) s = fmaf(__ldg(params + op.w_off + oo * D + g), bufG[oo * TPP + p], s);
+        dx[pt * D + g] = s;
+      }
 
       // (4) grad wrt this op's input: C[j][i][p] = sum_o W[o][i] zbar[j][o][p] (+ skip branch)
       if (need_dinput) {
@@ -344,7 +351,6 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
     }
     __syncthreads();
   }
-  (void)dx;
 }
 
 // dparams[i] += sum_c part[c][i]

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ params,
            const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
            const float* __restrict__ dout, const float* __restrict__ stash, int64_t n_pad,
-           float* __restrict__ part_all, int64_t n_params, float* __restrict__ skipbar_all, int n_tiles) {
+           float* __restrict__ part_all, int64_t n_params, float* __restrict__ skipbar_all,
+           float* __restrict__ dx, int n_tiles) {
   constexpr int J = 1 + ORDER * D;
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
   constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
@@ -629,6 +630,18 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
         }
       }
+      // gradient w.r.t. the points: x enters the network only through the value channel of op 0
+      // (z = W x + b; dz_i/dx = 0), so dL/dx_i = sum_f W[f][i] zbar_0[f]; the four feature quarters of a point
+      // meet in global memory (dx is zeroed by the caller of the kernel)
+      if (dx != nullptr && valid) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          float s = 0.0f;
+#pragma unroll
+          for (int e = 0; e < kFpt; ++e) s = fmaf(__ldg(params + op.w_off + (f0 + e) * D + i), zb0[e], s);
+          atomicAdd(dx + pt * D + i, s);
+        }
+      }
       {
         const int fr = f0 + (lane >> 1);
         const bool w = (lane & 1) == 0;
@@ -682,7 +695,8 @@ template <int D, int ORDER, int FEAT>
 static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, const float* packed,
                                    const float* x, int64_t n, const float* dout, const float* stash,
                                    int64_t n_pad, float* part, int max_slabs, int64_t n_params,
-                                   float* dparams, float* skip_scratch, int sm_count, cudaStream_t stream) {
+                                   float* dparams, float* dx, float* skip_scratch, int sm_count,
+                                   cudaStream_t stream) {
   auto kern = jet_bwd_tc<D, ORDER, FEAT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdSmem::kTotal);
   if (e != cudaSuccess) return e;
@@ -693,7 +707,7 @@ static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, con
   if ((reinterpret_cast<uintptr_t>(part) & 15) != 0) return cudaErrorMisalignedAddress;
   if (grid > 148) grid = 148;   // the skip scratch holds 148 CTA regions
   kern<<<grid, kTcThreads, TcBwdSmem::kTotal, stream>>>(prog, params, packed, x, n, dout, stash, n_pad, part,
-                                                         n_params, skip_scratch, n_tiles);
+                                                         n_params, skip_scratch, dx, n_tiles);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   fold_partials_tc<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, dparams);
@@ -704,9 +718,13 @@ cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float*
                           int64_t n, int d, int order, const float* dout, const float* stash, int64_t n_pad,
                           float* part, int max_slabs, int64_t n_params, float* dparams, float* dx,
                           float* skip_scratch, int sm_count, cudaStream_t stream) {
-  if (dx != nullptr) return cudaErrorNotSupported;
   const int feat = tc_feat(prog);
-#define TC_BWD_ARGS (prog, params, packed, x, n, dout, stash, n_pad, part, max_slabs, n_params, dparams, skip_scratch, sm_count, stream)
+  if (dx != nullptr) {
+    if (feat == 2) return cudaErrorNotSupported;   // (checked with a message at the C ABI)
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)n * d * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+  }
+#define TC_BWD_ARGS (prog, params, packed, x, n, dout, stash, n_pad, part, max_slabs, n_params, dparams, dx, skip_scratch, sm_count, stream)
 #define TC_BWD(D_, O_)                                            \
   if (d == D_ && order == O_) {                                   \
     if (feat == 0) return launch_bwd_tc_t<D_, O_, 0> TC_BWD_ARGS; \

@@ -86,13 +86,13 @@ class CudaBackend:
         CudaBackend.gpu_launches += 1
 
     def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace,
-                     engine=_lib.ENGINE_AUTO):
+                     engine=_lib.ENGINE_AUTO, dx=None):
         p, k = self._ops(ops)
         n, d = x.shape
         tok = self._timed("bwd", n, order)
         _lib.check(self.lib.mpinn_jet_backward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
                                                n, d, order, self._ptr(dout), self._ptr(stash),
-                                               self._ptr(dparams), dparams.numel(), None,
+                                               self._ptr(dparams), dparams.numel(), self._ptr(dx),
                                                self._ptr(workspace),
                                                workspace.numel() * workspace.element_size(), engine,
                                                self._stream()), "mpinn_jet_backward")
@@ -149,6 +149,9 @@ class JetEngine:
         self.d = int(self.ops[0, 1])
         self.n_out = int(self.ops[-1, 2])
         self.kernel_engine = _lib.ENGINE_AUTO
+        # opt-in: also produce dL/d(points) in the reverse pass, so that `points.grad` is populated like the
+        # reference's backward() does (only its adversarial point generator reads it)
+        self.points_grad = False
         self.flat: Optional[torch.Tensor] = None
         self.flat_grad: Optional[torch.Tensor] = None
         self.packed: Optional[torch.Tensor] = None
@@ -252,13 +255,15 @@ class JetEngine:
         b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine)
         return out, stash
 
-    def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor):
-        """Returns the flat parameter gradient [P] for dL/d(out jets) = dout."""
+    def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor, want_dx: bool = False):
+        """Returns the flat parameter gradient [P] for dL/d(out jets) = dout -- and, with ``want_dx``, also the
+        gradient w.r.t. the points [N, d] (what the reference's ``backward()`` leaves in ``points.grad``)."""
         b = backend()
         if self.workspace is None or self.workspace.device != x.device:
             nbytes = b.workspace_bytes(self.ops, self.flat.numel())
             self.workspace = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
         dflat = torch.zeros_like(self.flat_grad)
+        dx = torch.empty_like(x) if want_dx else None
         b.jet_backward(self.ops, self.flat.detach(), self.packed, x, order, dout, stash, dflat,
-                       self.workspace, self.kernel_engine)
-        return dflat
+                       self.workspace, self.kernel_engine, dx)
+        return (dflat, dx) if want_dx else dflat

@@ -156,6 +156,9 @@ class _JetFunction(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dout):
         x, stash = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            dflat, dx = ctx.engine.backward(x, ctx.order, dout.contiguous(), stash, want_dx=True)
+            return dflat, dx, None, None
         dflat = ctx.engine.backward(x, ctx.order, dout.contiguous(), stash)
         return dflat, None, None, None
 
@@ -171,6 +174,8 @@ def _run_block(engine, arg: torch.Tensor, order: int, plan, plan_idx) -> torch.T
         raise RuntimeError(f"points are on {x.device} but the model is on {engine.flat.device}")
     x = x.contiguous()
     if torch.is_grad_enabled() and engine.flat.requires_grad:
+        if engine.points_grad and arg.requires_grad:
+            x = arg.contiguous()   # stays in the autograd graph: the reverse pass also returns dL/d(points)
         out = _JetFunction.apply(engine.flat, x, engine, order)
     else:
         out, _ = engine.forward(x, order, need_stash=False)

@@ -35,11 +35,13 @@ class OracleBackend:
         o, _ = JR.forward(ops, self._np(params), self._np(x), order)
         out.copy_(torch.from_numpy(np.ascontiguousarray(o.transpose(1, 0, 2))).to(out.dtype))
 
-    def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace, engine=0):
+    def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace, engine=0, dx=None):
         self.calls.append(("bwd", int(order), int(x.shape[0])))
         p, xx = self._np(params), self._np(x)
         _, cache = JR.forward(ops, p, xx, order)
-        dp, _ = JR.backward(ops, p, xx, order, cache, self._np(dout).transpose(1, 0, 2))
+        dp, dxx = JR.backward(ops, p, xx, order, cache, self._np(dout).transpose(1, 0, 2))
+        if dx is not None:
+            dx.copy_(torch.from_numpy(np.ascontiguousarray(dxx)).to(dx.dtype))
         # frozen Fourier encodings get no gradient from the fused reverse pass
         ops = np.asarray(ops).reshape(-1, 8)
         if ops[0, 0] == JR.OP_FOURIER:

@@ -316,3 +316,28 @@ def test_constant_losses(oracle_backend):
     assert relerr(total.item(), float((g["losses_f64"] * np.array(lam)).sum())) < 1e-5
     with pytest.raises(Exception):
         mp.ConstantLosses([1.0])(tr)
+
+
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "burgers_1D", "navier_stokes_2D"])
+def test_points_grad_matches_reference_backward(name, oracle_backend):
+    """Opt-in `points_grad`: after backward() every condition's `points.grad` equals what the reference's nested
+    autograd leaves there (reference trainer/trainer.py:141 differentiates w.r.t. the points as a side effect;
+    generation/grad_based_generator.py:66 reads it)."""
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    model.jet_engine.points_grad = True
+    pinn.select_batch(0)
+    total, _ = pinn.calculate_mean_loss()
+    total.backward()
+    # the reference algorithm, fp64, same weights and points
+    fn, kind, _ = problems.CONFIGS[name]
+    spec, din, dout = fn(types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack, Symbols=None))
+    ref = AR.MODELS[kind](int(g["input_dim"]), int(g["output_dim"]), **GOLD_KW[name]).double()
+    ref.load_state_dict({k: torch.tensor(g["w::" + k]).double() for k in g["state_keys"]})
+    pts = [torch.tensor(g[f"pts{i}"]).double().requires_grad_() for i in range(len(spec))]
+    res = [r for (f, _), x in zip(spec, pts) for r in f(ref, x)]
+    # "mean" loss: all squared residual entries over their total count (reference PINN/PINN.py:112-125)
+    (sum((r ** 2).sum() for r in res) / sum(r.numel() for r in res)).backward()
+    for c, x in zip(conds, pts):
+        assert c.points.grad is not None
+        assert relerr(c.points.grad.numpy(), x.grad.numpy()) < 1e-5

@@ -231,7 +231,9 @@ def run_ours(args):
     pinn = mp.PINN(model, conds)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
-    calc_loss = mp.GradientLosses(alpha=0.9) if args.regularization == "gradient" else "mean"
+    calc_loss = {"none": lambda: "mean", "gradient": lambda: mp.GradientLosses(alpha=0.9),
+                 "normal": lambda: mp.NormalLosses(alpha=0.9),
+                 "pointwise": lambda: mp.PointwiseLosses()}[args.regularization]()
     if world > 1:
         trainer = mp.TrainerMultiGPU(pinn, opt, sched, num_epochs=10**9, num_batches=world,
                                      update_grid_every=10**9, calc_loss=calc_loss, rank=rank,
@@ -430,7 +432,7 @@ def main():
     ap.add_argument("--domain-points", type=int, default=0)
     ap.add_argument("--bound-points", type=int, default=0)
     ap.add_argument("--no-baselines", action="store_true")
-    ap.add_argument("--regularization", default="none", choices=["none", "gradient"],
+    ap.add_argument("--regularization", default="none", choices=["none", "gradient", "normal", "pointwise"],
                     help="calc_loss: 'none' = \"mean\" (the BASELINE metric); 'gradient' = GradientLosses(0.9), "
                          "the shipped default of poisson_2D_1C (secondary number)")
     args = ap.parse_args()

@@ -207,9 +207,11 @@ def run_case(mp, name, modname, factory, model_name, kwargs, counts):
     return out
 
 
-def gradient_reg_case(mp):
-    """Reference GradientLosses(alpha=0.9) (regularization/gradient.py:25-59), poisson_2D_1C's shipped default:
-    3 TrainerOneBatch steps from the poisson golden weights/points; lambdas, losses and weights per step."""
+def gradient_reg_case(mp, kind="gradient"):
+    """Reference GradientLosses(alpha=0.9) (regularization/gradient.py:25-59), poisson_2D_1C's shipped default --
+    or NormalLosses(alpha=0.9) (regularization/normal.py:6-45) / PointwiseLosses(lr=0.01)
+    (regularization/pointwise.py:9-152): 3 TrainerOneBatch steps from the poisson golden weights/points; lambdas,
+    losses and weights per step."""
     g = np.load(os.path.join(HERE, "poisson_2D_1C.npz"))
     mod = importlib.import_module("examples.poisson_2D_1C.problem")
     conds, din, dout = mod.poisson_2D_1C()
@@ -221,14 +223,21 @@ def gradient_reg_case(mp):
         c.points, c.batch_size = p, len(p)
     pinn = mp.PINN(model=model, conditions=conds)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    reg = mp.regularization.GradientLosses(alpha=0.9)
+    reg = {"gradient": lambda: mp.regularization.GradientLosses(alpha=0.9),
+           "normal": lambda: mp.regularization.NormalLosses(alpha=0.9),
+           "pointwise": lambda: mp.regularization.PointwiseLosses(ignored_indexes=[1], lr=0.01)}[kind]()
     tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg,
                             callbacks_organizer=mp.CallbacksOrganizer([]))
     out = {"lambdas": [], "totals": [], "losses": []}
     for e in range(3):
         tr.current_epoch = e + 1
         tr._train_epoch()
-        out["lambdas"].append(reg.lambda_regularization.detach().numpy().copy())
+        if kind == "pointwise":   # per-point weights of residual 0 (a sample) and of the last residual
+            ms = reg.models[0]
+            out["lambdas"].append(np.concatenate([ms[0].weight.detach().numpy().reshape(-1)[:16],
+                                                  ms[-1].weight.detach().numpy().reshape(-1)[:16]]))
+        else:
+            out["lambdas"].append(reg.lambda_regularization.detach().numpy().copy())
         out["totals"].append(float(tr.total_loss))
         out["losses"].append(tr.epoch_loss_detailed.numpy().copy())
     out = {k: np.array(v) for k, v in out.items()}
@@ -257,10 +266,11 @@ def main():
         np.savez_compressed(path, **out)
         print(case[0], "total_f32", out["total_f32"], "total_f64", out["total_f64"],
               os.path.getsize(path) // 1024, "KiB")
-    if not only or "gradient_reg" in only:
-        out = gradient_reg_case(mp)
-        np.savez_compressed(os.path.join(HERE, "poisson_gradient_reg.npz"), **out)
-        print("gradient_reg lambdas", out["lambdas"][-1], "totals", out["totals"])
+    for kind in ("gradient", "normal", "pointwise"):
+        if not only or f"{kind}_reg" in only:
+            out = gradient_reg_case(mp, kind)
+            np.savez_compressed(os.path.join(HERE, f"poisson_{kind}_reg.npz"), **out)
+            print(f"{kind}_reg lambdas", out["lambdas"][-1][:6], "totals", out["totals"])
 
 
 if __name__ == "__main__":

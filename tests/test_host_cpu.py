@@ -305,6 +305,51 @@ def test_gradient_losses_matches_reference(oracle_backend):
     assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
 
 
+def test_normal_losses_matches_reference(oracle_backend):
+    """NormalLosses(alpha=0.9) follows the reference's lambdas, totals, losses and weights over 3 steps
+    (reference regularization/normal.py:6-45), with ONE reverse launch per condition."""
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", "poisson_normal_reg.npz"))
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.NormalLosses(alpha=0.9)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    for e in range(3):
+        tr.current_epoch = e + 1
+        oracle_backend.calls.clear()
+        tr._train_epoch()
+        assert sum(1 for c in oracle_backend.calls if c[0] == "bwd") == len(conds)
+        assert relerr(reg.lambda_regularization.numpy(), gr["lambdas"][e]) < 2e-4
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 1e-5
+        assert relerr(tr.epoch_loss_detailed.numpy(), gr["losses"][e]) < 1e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
+
+
+def test_pointwise_losses_matches_reference(oracle_backend):
+    """PointwiseLosses(ignored_indexes=[1], lr=0.01): per-point weights after each maximising Adam step, weighted
+    totals, reported losses and network weights over 3 steps (reference regularization/pointwise.py:9-152); the
+    residuals are evaluated once per step here (one forward per condition)."""
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", "poisson_pointwise_reg.npz"))
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.PointwiseLosses(ignored_indexes=[1], lr=0.01)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    for e in range(3):
+        tr.current_epoch = e + 1
+        oracle_backend.calls.clear()
+        tr._train_epoch()
+        assert sum(1 for c in oracle_backend.calls if c[0] == "fwd") == len(conds)
+        ms = reg.models[0]
+        assert ms[1] is None and reg.ignored_mask[1]
+        lam = np.concatenate([ms[0].weight.detach().numpy().reshape(-1)[:16],
+                              ms[-1].weight.detach().numpy().reshape(-1)[:16]])
+        assert relerr(lam, gr["lambdas"][e]) < 1e-5
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 1e-5
+        assert relerr(tr.epoch_loss_detailed.numpy(), gr["losses"][e]) < 1e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
+
+
 def test_constant_losses(oracle_backend):
     g = load("poisson_2D_1C")
     model, conds, pinn = build_pinn("poisson_2D_1C", g)

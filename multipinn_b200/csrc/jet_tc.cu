@@ -266,15 +266,23 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       // One channel of the source layer.  The channel index is a compile-time constant (the J calls below
       // are J specialised copies): which of the three activation-jet formulas applies, the TMEM block, the
       // stash plane and the A buffer are all resolved by the compiler instead of per-element branches.
-      auto channel = [&](auto idx_c) {
-        constexpr int idx = decltype(idx_c)::value;
+      // (With seven channels that many copies thrash the instruction cache: then only the channel KIND is the
+      // compile-time constant -- three copies -- and the direction is a run-time value.  `spec_c` = IC<idx> or
+      // IC<-1 - kind>.)
+      auto channel = [&](auto spec_c, const int dir_rt) {
+        constexpr int spec = decltype(spec_c)::value;
+        constexpr int idx_ct = spec >= 0 ? spec : 0;
         // production order: value, then (first, second) derivative per direction
-        constexpr int j = (idx == 0) ? 0
-                          : (ORDER == 2 ? (((idx - 1) & 1) ? 1 + D + ((idx - 1) >> 1) : 1 + ((idx - 1) >> 1)) : idx);
-        constexpr bool is_first = (j >= 1 && j <= D);
-        constexpr bool is_second = (j > D);
-        constexpr int dir = is_first ? j - 1 : (is_second ? j - 1 - D : 0);
-        constexpr int buf = idx & 1;
+        constexpr int j_ct = (idx_ct == 0) ? 0
+                             : (ORDER == 2 ? (((idx_ct - 1) & 1) ? 1 + D + ((idx_ct - 1) >> 1) : 1 + ((idx_ct - 1) >> 1))
+                                           : idx_ct);
+        constexpr int kind = spec >= 0 ? (j_ct == 0 ? 0 : (j_ct <= D ? 1 : 2)) : -1 - spec;
+        constexpr bool is_first = (kind == 1);
+        constexpr bool is_second = (kind == 2);
+        const int dir = spec >= 0 ? (is_first ? j_ct - 1 : (is_second ? j_ct - 1 - D : 0)) : dir_rt;
+        const int j = spec >= 0 ? j_ct : (kind == 0 ? 0 : (is_first ? 1 + dir : 1 + D + dir));
+        const int idx = spec >= 0 ? idx_ct : (kind == 0 ? 0 : (ORDER == 2 ? 1 + 2 * dir + (kind - 1) : 1 + dir));
+        const int buf = idx & 1;
         uint8_t* at = smem + (buf ? TcSmem::kA1 : TcSmem::kA0);
 #pragma unroll
         for (int c = 0; c < kFpt / 8; ++c) {
@@ -283,7 +291,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
-              if (j == 0) {
+              if (kind == 0) {
                 float v = bias_s[ST_B * kTcW + f];
 #pragma unroll
                 for (int i = 0; i < D; ++i)
@@ -297,7 +305,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             }
           } else {
             tmem_ld8(tmem + lane_base + BLK(j) * kTcW + f0 + c * 8, z);
-            if (j == 0) {
+            if (kind == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) z[e] += bias_s[ST_B * kTcW + f0 + c * 8 + e];
             }
@@ -311,7 +319,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           for (int e = 0; e < 8; ++e) {
             const int ff = c * 8 + e;
             zst[(j * kTcW + f0 + ff) * 128] = z[e];          // stash for the reverse pass
-            if (j == 0) {
+            if (kind == 0) {
               float c0, c1, c2, c3;
               act_coeffs<false>(act_src, z[e], c0, c1, c2, c3);
               s1[ff] = c1;
@@ -348,7 +356,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         __syncthreads();
         // blocks of the source layer that nobody needs any more
         if (S >= 1) {
-          if (j == 0) free_mask |= 1u << BLK(0);
+          if (kind == 0) free_mask |= 1u << BLK(0);
           else if (ORDER == 1) free_mask |= 1u << BLK(j);
           else if (is_second) free_mask |= (1u << BLK(j)) | (1u << BLK(1 + dir));
         }
@@ -356,7 +364,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         free_mask &= ~(1u << nb);
         nblk_p |= (uint32_t)nb << (4 * j);
         if (t == 0) {
-          if (idx == 0) {   // this layer's weight operand has landed
+          if (kind == 0) {   // this layer's weight operand has landed
             mbar_wait(&w_bar[ST_W], (st >> (2 + ST_W)) & 1u);
             st ^= 4u << ST_W;
           }
@@ -366,7 +374,20 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
         if (buf == 0) pending0 = 1; else pending1 = 1;
       };
-      static_for<0, J>(channel);
+      if constexpr (J <= 5) {
+        channel(IC<0>{}, 0);
+        if constexpr (J > 1) channel(IC<1>{}, 0);
+        if constexpr (J > 2) channel(IC<2>{}, 0);
+        if constexpr (J > 3) channel(IC<3>{}, 0);
+        if constexpr (J > 4) channel(IC<4>{}, 0);
+      } else {
+        channel(IC<-1>{}, 0);
+#pragma unroll 1
+        for (int dir = 0; dir < D; ++dir) {
+          channel(IC<-2>{}, dir);
+          if (ORDER == 2) channel(IC<-3>{}, dir);
+        }
+      }
       if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
       if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
       tc_fence_after_sync();

@@ -372,14 +372,22 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       // channel schedule: (d/dx_i, d2/dx_i2) per direction, value channel last
       // One phase = one channel.  The phase index is a compile-time constant (J specialised copies), so the
       // channel kind, TMEM columns and stash planes are resolved by the compiler, not by per-element branches.
-      auto phase = [&](auto step_c) {
-        constexpr int step = decltype(step_c)::value;
-        constexpr int jet = (step == J - 1) ? 0
-                            : (ORDER == 2 ? ((step & 1) ? 1 + D + (step >> 1) : 1 + (step >> 1)) : 1 + step);
-        constexpr bool is_first = (jet >= 1 && jet <= D);
-        constexpr bool is_second = (jet > D);
-        constexpr int dir = is_first ? jet - 1 : (is_second ? jet - 1 - D : 0);
+      // Up to five channels every phase gets its own specialised copy (the phase index is the compile-time
+      // constant).  With seven channels that much code thrashes the instruction cache, so only the channel KIND
+      // (value / first / second derivative) is a compile-time constant and the direction is a run-time value:
+      // three copies.  `spec_c` = IC<step> (>= 0) or IC<-1 - kind>.
+      auto phase = [&](auto spec_c, const int dir_rt, const bool first_rt) {
+        constexpr int spec = decltype(spec_c)::value;
+        constexpr int step = spec >= 0 ? spec : 0;
+        constexpr int jet_ct = (step == J - 1) ? 0
+                               : (ORDER == 2 ? ((step & 1) ? 1 + D + (step >> 1) : 1 + (step >> 1)) : 1 + step);
+        constexpr int kind = spec >= 0 ? (jet_ct == 0 ? 0 : (jet_ct <= D ? 1 : 2)) : -1 - spec;
+        constexpr bool is_first = (kind == 1);
+        constexpr bool is_second = (kind == 2);
         constexpr bool two = is_first && ORDER == 2;
+        const int dir = spec >= 0 ? (is_first ? jet_ct - 1 : (is_second ? jet_ct - 1 - D : 0)) : dir_rt;
+        const int jet = spec >= 0 ? jet_ct : (kind == 0 ? 0 : (is_first ? 1 + dir : 1 + D + dir));
+        const bool first_phase = spec >= 0 ? (step == 0) : first_rt;
 
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
         float zi_c[NC][8], zii_c[NC][8];
@@ -400,7 +408,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           // latency overlaps the zbar math (nothing between here and their use can be reordered by the
           // compiler across the barrier / tensor-memory instructions)
           float yi[8], yii[8];
-          if (jet != 0) {
+          if (kind != 0) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
@@ -427,7 +435,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int ff = c * 8 + e;
-              if (jet == 0) {
+              if (kind == 0) {
                 zb[e] = fmaf(ab[e], s1[ff], acc0[ff]);
               } else if (is_first) {
                 float v = ab[e] * s1[ff];
@@ -442,7 +450,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 zb[e] = ab[e] * s1[ff];
               }
             }
-            if (jet == 0) {
+            if (kind == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) zb0all[c * 8 + e] = zb[e];
             }
@@ -456,9 +464,9 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           // ---------------- activation jet channel of layer l-1 ----------------
           {
             float av[8];
-            if (jet == 0 && TCACHE) {
+            if (kind == 0 && TCACHE) {
               tmem_ld8(tmem + lane_base + kT0Col + f0 + c * 8, av);
-            } else if (jet == 0) {
+            } else if (kind == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 float t1, t2, t3;
@@ -503,7 +511,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(hq[c][q][0], hq[c][q][1], hq[c][q][2], hq[c][q][3]);
           }
         }
-        if (jet == 0) {
+        if (kind == 0) {
           static_assert(kFpt == 16, "warp_sum16 reduces exactly 16 features per thread");
           const float tot = warp_sum16(zb0all, lane);
           if ((lane & 1) == 0) bsum_s[warp * 16 + (lane >> 1)] = tot;
@@ -514,7 +522,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         __syncthreads();
         TC_TIME(5);     // phase barrier
         if (t == 0) {            // one lane of warp 0 issues the input-gradient GEMM ...
-          if (step == 0) {       // this layer's W^T operand has landed (bit 1 of bar_phase: parity of w_bar)
+          if (first_phase) {     // this layer's W^T operand has landed (bit 1 of bar_phase: parity of w_bar)
             mbar_wait(&w_bar, (bar_phase >> 1) & 1);
             bar_phase ^= 2;
           }
@@ -530,7 +538,20 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         dw_acc = 1;
         pending = 1;
       };
-      static_for<0, J>(phase);
+      if constexpr (J <= 5) {
+        phase(IC<0>{}, 0, false);
+        if constexpr (J > 1) phase(IC<1>{}, 0, false);
+        if constexpr (J > 2) phase(IC<2>{}, 0, false);
+        if constexpr (J > 3) phase(IC<3>{}, 0, false);
+        if constexpr (J > 4) phase(IC<4>{}, 0, false);
+      } else {   // (first, second) derivative per direction, value channel last
+#pragma unroll 1
+        for (int dir = 0; dir < D; ++dir) {
+          phase(IC<-2>{}, dir, dir == 0);
+          if (ORDER == 2) phase(IC<-3>{}, dir, false);
+        }
+        phase(IC<-1>{}, 0, false);
+      }
       mbar_wait(&mma_bar, bar_phase & 1);
       TC_TIME(7);       // final GEMM wait of the layer
       bar_phase ^= 1;

@@ -183,17 +183,10 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int f = f0 + c * 8 + e;
-        if (TCACHE) {
-          float c1, c2;
-          act_coeffs<(ORDER >= 2)>(act, z[e], c0[e], c1, c2, c3[e]);
-          cache[f * 128 + p] = c1;
-          cache[(64 + f) * 128 + p] = c2;
-        } else {
-          float P, Q;
-          act_basis(act, z[e], P, Q);
-          cache[f * 128 + p] = P;
-          cache[(64 + f) * 128 + p] = Q;
-        }
+        float c1, c2;
+        act_coeffs<(ORDER >= 2)>(act, z[e], c0[e], c1, c2, c3[e]);
+        cache[f * 128 + p] = c1;
+        cache[(64 + f) * 128 + p] = c2;
       }
       if (TCACHE) {
         tmem_st8(tmem + lane_base + kT0Col + f0 + c * 8, c0);
@@ -201,11 +194,12 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       }
     }
   };
-  // s0..s3 of layer `op` for feature f (this thread's point) from whatever the caches hold
-  auto coeffs_at = [&](const DevOp& op, const float* tstash, int f, float& c0, float& c1, float& c2, float& c3) {
+  // With seven channels tensor memory has no room for s0 / s3: they are evaluated again from the stashed
+  // pre-activation where needed (s3 once per layer, s0 in the value phase); s1 / s2 always come from the cache.
+  auto s0_s3_at = [&](const DevOp& op, int act, const float* tstash, int f, float& c0, float& c3) {
     const float z0 = __ldg(tstash + (op.stash_plane + f) * 128);
-    act_from_basis<(ORDER >= 2)>(HAS_FOURIER ? act_of(op, f0) : op.act, z0, cache[f * 128 + p],
-                                 cache[(64 + f) * 128 + p], c0, c1, c2, c3);
+    float c1, c2;
+    act_coeffs<(ORDER >= 2)>(act, z0, c0, c1, c2, c3);
   };
   // sum a per-thread value over the warp's 32 points and add it to the CTA scratch row f, slot < 8
   auto reduce_into = [&](float v, int f, int slot) {
@@ -273,13 +267,10 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int f = f0 + c * 8 + e;
-          float s1, s2;
-          if (TCACHE) {
-            s1 = cache[f * 128 + p];
-            s2 = cache[(64 + f) * 128 + p];
-          } else {
+          const float s1 = cache[f * 128 + p], s2 = cache[(64 + f) * 128 + p];
+          if (!TCACHE) {
             float s3;
-            coeffs_at(pv, tstash, f, t0[e], s1, s2, s3);
+            s0_s3_at(pv, HAS_FOURIER ? act_of(pv, f0) : pv.act, tstash, f, t0[e], s3);
           }
           float a[J];
           a[0] = t0[e];
@@ -334,6 +325,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       const bool add_sb = HAS_SKIP && (prog.ops[l + 1].flags & MPINN_FLAG_SAVE_SKIP);  // abar^l gets the skip branch from above
       // first three derivatives of layer l's activation for this thread's features, from the cached basis
       float s1[kFpt], s2[kFpt], s3[kFpt], acc0[kFpt];
+      const int act_l = HAS_FOURIER ? act_of(op, f0) : op.act;
+      const int act_m = HAS_FOURIER ? act_of(pv, f0) : pv.act;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         float v3[8];
@@ -341,13 +334,13 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int ff = c * 8 + e, f = f0 + ff;
+          s1[ff] = cache[f * 128 + p];
+          s2[ff] = cache[(64 + f) * 128 + p];
           if (TCACHE) {
-            s1[ff] = cache[f * 128 + p];
-            s2[ff] = cache[(64 + f) * 128 + p];
             s3[ff] = v3[e];
           } else {
             float s0;
-            coeffs_at(op, tstash, f, s0, s1[ff], s2[ff], s3[ff]);
+            s0_s3_at(op, act_l, tstash, f, s0, s3[ff]);
           }
           acc0[ff] = 0.0f;
         }
@@ -469,21 +462,14 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             } else if (kind == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float t1, t2, t3;
-                coeffs_at(pv, tstash, f0 + c * 8 + e, av[e], t1, t2, t3);
+                float t3;
+                s0_s3_at(pv, act_m, tstash, f0 + c * 8 + e, av[e], t3);
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int f = f0 + c * 8 + e;
-                float t1, t2;
-                if (TCACHE) {
-                  t1 = cache[f * 128 + p];
-                  t2 = cache[(64 + f) * 128 + p];
-                } else {
-                  float t0, t3;
-                  coeffs_at(pv, tstash, f, t0, t1, t2, t3);
-                }
+                const float t1 = cache[f * 128 + p], t2 = cache[(64 + f) * 128 + p];
                 av[e] = is_first ? t1 * yi[e] : fmaf(t2 * yi[e], yi[e], t1 * yii[e]);
               }
             }
@@ -612,12 +598,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int f = f0 + c * 8 + e;
-          if (TCACHE) {
-            s1[e] = cache[f * 128 + p];
-            s2[e] = cache[(64 + f) * 128 + p];
-          } else {
+          s1[e] = cache[f * 128 + p];
+          s2[e] = cache[(64 + f) * 128 + p];
+          if (!TCACHE) {
             float s0;
-            coeffs_at(op, tstash, f, s0, s1[e], s2[e], s3[e]);
+            s0_s3_at(op, op.act, tstash, f, s0, s3[e]);
           }
           zb0[c * 8 + e] = ab0[e] * s1[e];
         }

@@ -385,6 +385,28 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
         float zi_c[NC][8], zii_c[NC][8];
         uint32_t zq[NC][3][4], hq[NC][3][4];   // this phase's bf16x3 operand pieces, stored after the GEMM wait
+        // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this phase
+        // touches, so they are waited for as late as possible: with ALL of this phase's math done and its bf16x3
+        // pieces in registers (kLateWait), or -- for the residual-block variant, which has the skip gradient's
+        // registers live as well and would spill -- after the first chunk's math.
+        constexpr bool kLateWait = (FEAT != 1);
+        auto wait_prev_gemms = [&]() {
+          TC_TIME(2);   // loads + math
+          if (pending) {
+            mbar_wait(&mma_bar, bar_phase & 1);
+            bar_phase ^= 1;
+            pending = 0;
+          }
+          TC_TIME(3);   // waiting for the previous phase's GEMMs
+        };
+        auto store_chunk = [&](int c) {
+          const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<uint4*>(z_tile + q * kBfRegion + off) = make_uint4(zq[c][q][0], zq[c][q][1], zq[c][q][2], zq[c][q][3]);
+            *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(hq[c][q][0], hq[c][q][1], hq[c][q][2], hq[c][q][3]);
+          }
+        };
         auto request_zl = [&](int c) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -477,25 +499,15 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             for (int e = 0; e < 4; ++e) split_bf16x3(av[2 * e], av[2 * e + 1], hq[c][0][e], hq[c][1][e], hq[c][2][e]);
             if (c + 1 < NC) request_zl(c + 1);
           }
-        }
-        // The GEMMs of the previous phase read both operand tiles but none of the TMEM columns this phase has
-        // touched, so they are waited for only now -- with all of this phase's math done and its bf16x3 pieces
-        // in registers -- right before the tiles are overwritten.
-        TC_TIME(2);   // loads + math
-        if (pending) {
-          mbar_wait(&mma_bar, bar_phase & 1);
-          bar_phase ^= 1;
-          pending = 0;
-        }
-        TC_TIME(3);   // waiting for the previous phase's GEMMs
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const uint32_t off = sw128_offset_bf16(p, f0 + c * 8);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            *reinterpret_cast<uint4*>(z_tile + q * kBfRegion + off) = make_uint4(zq[c][q][0], zq[c][q][1], zq[c][q][2], zq[c][q][3]);
-            *reinterpret_cast<uint4*>(h_tile + q * kBfRegion + off) = make_uint4(hq[c][q][0], hq[c][q][1], hq[c][q][2], hq[c][q][3]);
+          if (!kLateWait) {   // residual-block programs: store chunk by chunk (fewer live registers)
+            if (c == 0) wait_prev_gemms();
+            store_chunk(c);
           }
+        }
+        if (kLateWait) {
+          wait_prev_gemms();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) store_chunk(c);
         }
         if (kind == 0) {
           static_assert(kFpt == 16, "warp_sum16 reduces exactly 16 features per thread");

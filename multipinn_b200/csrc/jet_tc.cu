@@ -522,7 +522,7 @@ static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, con
   const int n_tiles = (int)((n + 127) / 128);
   int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (grid > 148) grid = 148;   // the skip scratch holds 148 CTA regions
-  kern<<<grid, kTcBlock, TcSmem::kTotal, stream>>>(prog, params, packed, x, n, out, stash, n_pad, n_tiles);
+  kern<<<grid, kTcThreads, TcSmem::kTotal, stream>>>(prog, params, packed, x, n, out, stash, n_pad, n_tiles);
   return cudaGetLastError();
 }
 

@@ -52,7 +52,6 @@ struct TcBwdSmem {
   static constexpr int kCache = kW + kBfWTile;               // basis values [2][64][128]    64 KiB
   static constexpr int kRed = kCache + 2 * 64 * 128 * 4;     // [64][8] reduction scratch      2 KiB
   static constexpr int kTotal = kRed + 64 * 8 * 4 + 16 * 16 * 4 + 1024;
-  static constexpr int kXchStride = 65;                      // dW half exchange aliases the a tile
 };
 
 // one thread asks the L2 to fetch `bytes` (multiple of 16) starting at p
@@ -131,7 +130,6 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   float* cache = reinterpret_cast<float*>(smem + TcBwdSmem::kCache);  // [2][64][128]
   float* red_s = reinterpret_cast<float*>(smem + TcBwdSmem::kRed);    // [64][8]
   float* bsum_s = red_s + 64 * 8;                                     // [16 warps][16] bias-gradient partials
-  float* xch = reinterpret_cast<float*>(h_tile);                      // [64][65] (only between GEMM groups)
   __shared__ uint64_t mma_bar;
   __shared__ uint64_t w_bar;      // the TMA engine drops each layer's W^T operand image into w_tile
   __shared__ uint32_t tmem_base_s;

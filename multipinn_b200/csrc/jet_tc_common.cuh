@@ -14,7 +14,6 @@ using namespace umma;
 constexpr int kTcW = 64;                 // layer width handled by this engine
 constexpr int kTcThreads = 512;          // 16 warps: 4 threads per point, 16 features each
 constexpr int kFpt = kTcW / (kTcThreads / 128);  // features per thread
-constexpr int kTcBlock = kTcThreads;
 constexpr int kTileRows = 128;
 constexpr int kRegionBytes = kTileRows * 128;       // [128 rows x 32 fp32]  = 16 KiB
 constexpr int kATileBytes = 4 * kRegionBytes;       // hi kb0, hi kb1, lo kb0, lo kb1 = 64 KiB
@@ -52,7 +51,6 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset_bf16(int row, int col)
 // MMA issue helpers (called by one thread)
 // ---------------------------------------------------------------------------------------------
 // Z[128 x 64] (+)= A[128 x 64] * B[64 x 64]^T, 3xTF32, A/B K-major tiles (hi kb0, hi kb1, lo kb0, lo kb1)
-template <bool ELECT = false>
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_tf32(128, 64, 0, 0);
   // descriptors differ only in their 14-bit start-address field (units of 16 bytes): build them once
@@ -70,8 +68,7 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_ti
     for (int ks = 0; ks < 8; ++ks) {
       const uint32_t a_off = a_base + (ks >> 2) * kRegionBytes + (ks & 3) * 32;
       const uint32_t b_off = b_base + (ks >> 2) * kWRegionBytes + (ks & 3) * 32;
-      if (ELECT) mma_tf32_ss_elect(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
-      else mma_tf32_ss(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
+      mma_tf32_ss(d_tmem, a0 + (a_off >> 4), b0 + (b_off >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -113,7 +110,6 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 }
 
 // D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major bf16x3 tiles; smallest products first
-template <bool ELECT = false>
 __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
   // (a piece, b piece): weights 2^-16 first, then 2^-8, then the leading product
@@ -127,8 +123,7 @@ __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {   // K = 16 bf16 = 32 bytes per MMA
       const uint64_t ad = a0 + ((pa[q] * kBfRegion + ks * 32) >> 4), bd = b0 + ((pb[q] * kBfWRegion + ks * 32) >> 4);
-      if (ELECT) mma_f16_ss_elect(d_tmem, ad, bd, idesc, acc);
-      else mma_bf16_ss(d_tmem, ad, bd, idesc, acc);
+      mma_bf16_ss(d_tmem, ad, bd, idesc, acc);
       acc = 1;
     }
   }
@@ -137,7 +132,6 @@ __device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_
 // D[128 x 64] (+)= stacked(Z)^T * H over the 128 rows (points) of the tiles, MN-major views.
 //   rows 0..63 : Z1^T (H1 + H2 + H3) + Z3^T H1        rows 64..127 : Z2^T (H1 + H2) (+ Z3^T H3, negligible)
 // Z tile regions: [Z1][Z2][Z3][ZERO]; H tile regions: [H1][H2][H3].  The caller adds the two halves.
-template <bool ELECT = false>
 __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
                                                      uint32_t accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
@@ -154,8 +148,7 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {   // K = 16 points = two 8-row swizzle atoms (SBO = 1024)
       const uint64_t zd = (zs[q] == 1 ? z1 : z2) + ((zr[q] * kBfRegion + ks * 2048) >> 4);
-      if (ELECT) mma_f16_ss_elect(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
-      else mma_bf16_ss(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
+      mma_bf16_ss(d_tmem, zd, h0 + ((hp[q] * kBfRegion + ks * 2048) >> 4), idesc, acc);
       acc = 1;
     }
   }

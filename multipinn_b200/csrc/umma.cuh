@@ -61,10 +61,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, u
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// barrier among the staging threads only (the MMA-issuing warp never joins it)
-__device__ __forceinline__ void stage_sync(int n_threads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
-}
 
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -123,41 +119,6 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
-// Warp-uniform variants for a dedicated issuing warp: all 32 lanes execute the same instruction stream
-// (so descriptors stay in uniform registers) and one elected lane performs the tcgen05 operation.
-__device__ __forceinline__ void mma_tf32_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                  uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-      "}\n" ::"r"(smem_u32(bar))
-      : "memory");
-}
 
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 // (implies tcgen05.fence::before_thread_sync)
@@ -207,26 +168,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};\n" ::"r"(
-          __float_as_uint(v[0])),
-      "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
-      "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
-      "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
-      "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])),
-      "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])),
-      "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
-      "r"(__float_as_uint(v[31])), "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 // ------------------------------------------------------------------------------------------ tile addressing
 // byte offset of element (row, col) inside a [rows x 32 fp32] swizzled region (region base 1024-aligned)

@@ -82,10 +82,13 @@ int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* param
                        float* dx, void* workspace, size_t workspace_bytes, int engine,
                        void* stream);
 
-/* Diagnostic: one 128x64x64 (mode 0, K-major operands: c = a[128][64] * b[64][64]^T) or 128x64x128
- * (mode 1, MN-major operands: c[128][64] = [hi(a)|lo(a)]^T * b with a,b [128][64]; rows 0..63 plus
- * rows 64..127 give a^T b) 3xTF32 tcgen05.mma product through the same descriptor/layout helpers the
- * jet kernels use.  Exists so the tensor-core conventions can be pinned in isolation by tests. */
+/* Diagnostic: one tcgen05.mma product through the same descriptor / layout / issue helpers the jet kernels use, so
+ * that the tensor-core conventions can be pinned in isolation by tests.
+ *   mode 0: c[128][64] = a[128][64] * b[64][64]^T, 3xTF32, K-major operands (forward pass)
+ *   mode 2: the same product as BF16x3 (three bf16 pieces per operand, six piece products), K-major (reverse pass)
+ *   mode 3: c[128][64] = stacked(a)^T b with a, b [128][64], BF16x3, MN-major operands; rows 0..63 plus rows
+ *           64..127 of c give a^T b (weight-gradient GEMM of the reverse pass)
+ * (mode 1, an MN-major TF32 variant, was removed: it needs a swizzle layout the kernels do not use.) */
 int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream);
 
 /* Diagnostic: when the library is built with -DMPINN_TC_TIMING=1 the tcgen05 reverse kernel accumulates

@@ -73,13 +73,17 @@ __device__ __forceinline__ void gelu_basis(float z, float& P, float& Q) {
   Q = (kGeluC * kInvSqrtPi) * e;
 }
 
+// sincosf carries a ~160-instruction large-argument path; inlined at every (unrolled) call site it was a fifth of
+// the reverse kernel's code although only the first layer uses it, so it is kept out of line.
+static __device__ __noinline__ void sincos_call(float z, float& s, float& c) { sincosf(z, &s, &c); }
+
 // The transcendental part of an activation at z, as two "basis" values from which s0..s3 follow with
 // a few FMAs:  GELU -> (Phi(z), phi(z)),  Sine -> (sin z, cos z).
 __device__ __forceinline__ void act_basis(int act, float z, float& P, float& Q) {
   if (act == MPINN_ACT_GELU) {
     gelu_basis(z, P, Q);
   } else if (act == MPINN_ACT_SINE || act == kActCos) {
-    sincosf(z, &P, &Q);
+    sincos_call(z, P, Q);
   } else {
     P = 0.0f;
     Q = 0.0f;

@@ -54,6 +54,20 @@ struct TcBwdSmem {
   static constexpr int kTotal = kRed + 64 * 8 * 4 + 16 * 16 * 4 + 1024;
 };
 
+// The two GEMMs of a phase, out of line (one copy instead of one per specialised phase) and with the operand
+// tiles addressed from the warp-uniform shared-memory base inside the function rather than through arguments:
+// descriptor arithmetic then stays on the uniform datapath instead of a register -> uniform-register move loop
+// around every MMA (21 -> ~8 instructions per MMA on the issuing threads, which the other warps wait for).
+extern __shared__ __align__(1024) uint8_t mpinn_bwd_smem_raw[];
+static __device__ __noinline__ void issue_input_gradient_gemm(uint32_t d_tmem) {
+  uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
+  issue_bf16x3_kmajor(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kW));
+}
+static __device__ __noinline__ void issue_weight_gradient_gemm(uint32_t d_tmem, uint32_t accumulate) {
+  uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
+  issue_bf16x3_mnmajor(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kH), accumulate);
+}
+
 // one thread asks the L2 to fetch `bytes` (multiple of 16) starting at p
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -122,8 +136,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   // the activation instead and s0..s3 are re-derived from them (a few FMAs + one z0 reload) where needed.
   constexpr bool TCACHE = (J * kTcW <= (int)kT0Col);
   constexpr int NC = kFpt / 8;      // 8-feature chunks per thread
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
   uint8_t* z_tile = smem + TcBwdSmem::kZ;
   uint8_t* h_tile = smem + TcBwdSmem::kH;
   uint8_t* w_tile = smem + TcBwdSmem::kW;
@@ -523,11 +536,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             bar_phase ^= 2;
           }
           tc_fence_after_sync();
-          issue_bf16x3_kmajor(tmem + jet * kTcW, smem_u32(z_tile), smem_u32(w_tile));
+          issue_input_gradient_gemm(tmem + jet * kTcW);
           mma_commit(&mma_bar);
         } else if (t == 32) {    // ... one lane of warp 1 the weight-gradient GEMM (independent accumulators)
           tc_fence_after_sync();
-          issue_bf16x3_mnmajor(tmem + kDwCol, smem_u32(z_tile), smem_u32(h_tile), dw_acc);
+          issue_weight_gradient_gemm(tmem + kDwCol, dw_acc);
           mma_commit(&mma_bar);
         }
         TC_TIME(6);     // MMA issue (thread 0 only)

@@ -110,7 +110,7 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 }
 
 // D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major bf16x3 tiles; smallest products first
-static __device__ __noinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
+__device__ __forceinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
   // (a piece, b piece): weights 2^-16 first, then 2^-8, then the leading product
   constexpr int pa[6] = {2, 1, 0, 1, 0, 0};
@@ -132,7 +132,7 @@ static __device__ __noinline__ void issue_bf16x3_kmajor(uint32_t d_tmem, uint32_
 // D[128 x 64] (+)= stacked(Z)^T * H over the 128 rows (points) of the tiles, MN-major views.
 //   rows 0..63 : Z1^T (H1 + H2 + H3) + Z3^T H1        rows 64..127 : Z2^T (H1 + H2) (+ Z3^T H3, negligible)
 // Z tile regions: [Z1][Z2][Z3][ZERO]; H tile regions: [H1][H2][H3].  The caller adds the two halves.
-static __device__ __noinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
+__device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
                                                      uint32_t accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
   // (first Z region, region stride between the two M halves, H piece)

@@ -356,8 +356,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           acc0[ff] = 0.0f;
         }
       }
-      for (int i = t; i < 64 * 8; i += kTcThreads) red_s[i] = 0.0f;
-      __syncthreads();                 // (the caches are thread-private; this orders red_s)
+      // (no barrier needed here: the coefficient caches are thread-private and red_s is not used by the GEMM layers)
       fill_cache(pv, tstash);          // now the cache holds layer l-1
 
       // the layer below will be needed next (its z as "z^l", and the one under it as "z^{l-1}"):

@@ -593,9 +593,15 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         part[op.b_off + t] += bsum_s[(q * 4 + 0) * 16 + k] + bsum_s[(q * 4 + 1) * 16 + k] +
                               bsum_s[(q * 4 + 2) * 16 + k] + bsum_s[(q * 4 + 3) * 16 + k];
       }
-      tc_fence_before_sync();
-      __syncthreads();
-      tc_fence_after_sync();
+      // A block barrier is needed here only with a single channel: then the next layer's one phase writes the
+      // bias partials (bsum_s) that warps 0-1 may still be reading above.  With more channels at least one phase
+      // barrier lies in between; the dW accumulator columns read above are not overwritten before the next
+      // layer's first phase barrier either, and everything else a layer touches is thread-private.
+      if (J == 1) {
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+      }
       TC_TIME(8);       // dW flush
     }
 

@@ -356,7 +356,7 @@ def run_ours(args):
                         "peak_source": peak_src,
                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
                         # capture of this exact workload (profiles/r1_tc_ncu_summary.txt); null elsewhere
-                        "traffic": (14.456353e9 + 1.167733e9) if (args.workload == "poisson_2D_1C" and
+                        "traffic": (14.334291e9 + 1.166608e9) if (args.workload == "poisson_2D_1C" and
                                                                    args.engine == "auto" and
                                                                    n_domain == 1_000_000) else None,
                         "traffic_unit": "bytes per launch",

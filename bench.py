@@ -9,7 +9,8 @@ calc_loss="mean", Adam(1e-3), synthetic uniform points, random-init weights (see
 every rank holds that many points; `value` = all ranks' points / max-over-ranks step time.
 
 One JSON line on stdout (rank 0).  `--impl reference` times the reference's algorithm (nested
-torch.autograd, oracle/autograd_ref.py) on the host CPU cores on a bounded sample.
+torch.autograd with TorchScript-fused activations, oracle/autograd_ref.py) on the host CPU cores on a bounded
+sample (100 000 domain points).
 """
 import argparse
 import json
@@ -104,8 +105,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's algorithm on host cores
 # --------------------------------------------------------------------------------------------------
-def reference_cpu_run(workload, steps, warmup, n_domain, n_bound, device="cpu"):
-    """points/s of the nested-autograd step (oracle/autograd_ref.py) on `device`."""
+def reference_model_and_points(workload, n_domain, n_bound, device, state_dict=None, points=None):
     from oracle import autograd_ref as AR
 
     key = WORKLOADS[workload][0]
@@ -114,9 +114,19 @@ def reference_cpu_run(workload, steps, warmup, n_domain, n_bound, device="cpu"):
     spec, din, dout = fn(ns)
     torch.manual_seed(SEED)
     model = AR.MODELS[kind](din, dout, **kw).to(device)
-    rng = np.random.default_rng(SEED)
-    pts = [torch.tensor(p, device=device).requires_grad_() for p in sample_all(spec, n_domain, n_bound, rng)]
-    fns = [f for f, _ in spec]
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    if points is None:
+        rng = np.random.default_rng(SEED)
+        points = sample_all(spec, n_domain, n_bound, rng)
+    pts = [torch.as_tensor(p, device=device).detach().clone().requires_grad_() for p in points]
+    return AR, model, [f for f, _ in spec], pts
+
+
+def reference_cpu_run(workload, steps, warmup, n_domain, n_bound, device="cpu", scripted=True):
+    """points/s of the reference's nested-autograd train step (oracle/autograd_ref.py) on `device`."""
+    AR, model, fns, pts = reference_model_and_points(workload, n_domain, n_bound, device)
+    AR.SCRIPTED = scripted
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     n_points = sum(len(p) for p in pts)
     for _ in range(warmup):
@@ -129,7 +139,15 @@ def reference_cpu_run(workload, steps, warmup, n_domain, n_bound, device="cpu"):
     if device != "cpu":
         torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    AR.SCRIPTED = True
     return n_points / dt, dt * 1e3, n_points, float(total)
+
+
+def cpu_sample_sizes(workload):
+    """Bounded CPU sample: BASELINE.md section 3.3's 100 000 domain points (+ 5 000 per boundary condition)."""
+    if workload == "regression_1D":
+        return 256, 256
+    return 100_000, 5_000
 
 
 def run_reference(args):
@@ -138,18 +156,18 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nd, nb = 20_000, 1_000
-    if args.workload == "regression_1D":
-        nd = nb = 256
+    nd, nb = cpu_sample_sizes(args.workload)
     value, ms, n_points, _ = reference_cpu_run(args.workload, args.steps, args.warmup, nd, nb)
-    sample = f"{nd} domain + {nb} per boundary condition points per step ({n_points} total), fp32, torch CPU"
+    sample = (f"{nd} domain + {nb} per boundary condition points per step ({n_points} total), fp32, torch CPU, "
+              f"{args.steps} timed steps after {args.warmup} warm-up")
     line = {
         "impl": "reference", "metric": "collocation points/sec per full train step",
-        "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "value": value, "unit": "points/s", "n_gpus": 1, "requested_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "sample": sample,
-                   "algorithm": "nested torch.autograd.grad + backward + Adam (oracle/autograd_ref.py port)"},
+                   "algorithm": "nested torch.autograd.grad + backward + Adam, TorchScript-fused activations as in the "
+                                "reference (oracle/autograd_ref.py port); ONE CPU process whatever --gpus says"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": torch.get_num_threads(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,11 +200,23 @@ def tf32_matmul_peak():
         return None
 
 
+def ncu_traffic(workload, n_domain, kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture of this command
+    (profiles/r2_ncu_traffic.json, written by scripts/ncu_traffic.py from one `ncu --set full` run); None if the
+    capture does not cover this workload / size."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        ent = tab.get(f"{workload}:{n_domain}", {}).get(kernel)
+        return ent
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
 
     import multipinn_b200 as mp
-    from multipinn_b200 import _lib, engine
+    from multipinn_b200 import _lib, engine, trace
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -198,6 +228,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.no_laplace:
+        trace.ENABLE_LAPLACE = False
 
     key, n_domain, n_bound = WORKLOADS[args.workload]
     if args.domain_points:
@@ -212,7 +244,8 @@ def run_ours(args):
     model.jet_engine.kernel_engine = {"auto": _lib.ENGINE_AUTO, "ffma": _lib.ENGINE_FFMA,
                                       "tcgen05": _lib.ENGINE_TCGEN05}[args.engine]
     rng = np.random.default_rng(SEED + rank)  # only the local shard is generated
-    host_pts = [torch.from_numpy(p).pin_memory() for p in sample_all(spec, n_domain, n_bound, rng)]
+    host_np = sample_all(spec, n_domain, n_bound, rng)
+    host_pts = [torch.from_numpy(p).pin_memory() for p in host_np]
     dev_pts = [p.to(dev, non_blocking=True).requires_grad_() for p in host_pts]
 
     class _Gen:  # hands the resident device points to the Condition (no regeneration while timing)
@@ -241,9 +274,27 @@ def run_ours(args):
     else:
         trainer = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=10**9, update_grid_every=10**9,
                                      calc_loss=calc_loss)
+    trainer.use_fused_step = not args.no_fused
+    trainer.use_cuda_graphs = not args.no_graphs
     pinn.update_data()
     local_points = sum(len(p) for p in dev_pts)
     global_points = local_points * world
+    fs = trainer.fused_step()
+    programs = [c.program_for(model) for c in conds]
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    # ---------------- step-0 loss and flat gradient of this arm (compared with the reference algorithm below)
+    ours0 = None
+    if world == 1 and rank == 0 and not args.no_baselines:
+        pinn.select_batch(0)
+        if fs is not None:
+            fs.compute()
+            tot0, _ = fs.losses()
+        else:
+            model.jet_engine.zero_grad()
+            tot0, _ = pinn.calculate_mean_loss()
+            tot0.backward()
+        ours0 = (float(tot0), model.jet_engine.flat_grad.detach().clone())
 
     def step(epoch):
         trainer.current_epoch = epoch
@@ -267,7 +318,6 @@ def run_ours(args):
 
     # ---------------- timed region: K steps, inputs resident in HBM
     barrier()
-    engine.CudaBackend.timings = []
     launches0 = engine.CudaBackend.gpu_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -278,11 +328,10 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = engine.CudaBackend.gpu_launches - launches0
-    timings = engine.CudaBackend.timings
-    engine.CudaBackend.timings = None
     ms = e0.elapsed_time(e1) / args.steps
     clock_info = clocks.stop() if rank == 0 else None
     final_loss = float(trainer.total_loss)
+    graph_replays = fs.graph_replays if fs is not None else 0
 
     # ---------------- e2e: same step through the public API with HOST inputs (pinned) + loss readback
     # Every step's points come from pinned host memory.  The copy of step k+1's points runs on a second stream
@@ -324,17 +373,39 @@ def run_ours(args):
     h2d = sum(p.numel() * 4 for p in host_pts)
     d2h = 4 * (1 + int(trainer.epoch_loss_detailed.numel()))
 
+    # ---------------- attribution pass: the same step launched kernel by kernel (no graph) with CUDA events
+    # around every launch of ours, to get the dominant kernel's average duration
+    trainer.use_cuda_graphs = False
+    engine.CudaBackend.timings = []
+    for _ in range(3):
+        step(epoch)
+        epoch += 1
+    torch.cuda.synchronize()
+    timings = engine.CudaBackend.timings
+    engine.CudaBackend.timings = None
+    trainer.use_cuda_graphs = not args.no_graphs
+
     t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
 
     if rank == 0:
-        # dominant kernel: the reverse pass over the domain condition (order-2 jets)
+        # dominant kernel: the reverse pass over the domain condition
         Pw = weight_elems(model)
-        J = 1 + 2 * din
-        bwd = [a[3].elapsed_time(a[4]) for a in timings if a[0] == "bwd" and a[1] == n_domain and a[2] == 2]
-        fwd = [a[3].elapsed_time(a[4]) for a in timings if a[0] == "fwd" and a[1] == n_domain and a[2] == 2]
+        J_ref = 1 + 2 * din          # channels of the reference formulation ("J used")
+        dom_orders = ([b.order for b in programs[0].blocks] if programs[0] is not None
+                      else conds[0].plan_for(model).orders)
+        order_dom = max(dom_orders)
+        J_exec = model.jet_engine.n_jets(order_dom)
+        per_kind = {}
+        for a in timings:
+            per_kind.setdefault((a[0], a[1], a[2]), []).append(a[3].elapsed_time(a[4]))
+        avg = {k: sum(v) / len(v) for k, v in per_kind.items()}
+        bwd_ms = avg.get(("bwd", n_domain, order_dom))
+        fwd_ms = avg.get(("fwd", n_domain, order_dom))
+        res_ms = avg.get(("resid", n_domain, 0))
+        kernel_ms_per_step = sum(sum(v) for v in per_kind.values()) / 3.0
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -344,37 +415,41 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained bf16"
         tf32_peak = tf32_matmul_peak()
         roofline = None
-        if bwd:
-            bwd_ms = sum(bwd) / len(bwd)
-            flops = n_domain * J * 4 * Pw
+        if bwd_ms:
+            flops = n_domain * J_ref * 4 * Pw
             hidden = sum(int(r[2]) for r in model.jet_program()[:-1])   # stashed pre-activation features per point
-            stash_bytes = n_domain * J * hidden * 4
+            stash_bytes = n_domain * J_exec * hidden * 4
             hbm_peak = peaks.get("hbm_gbs", 6500.0)
             ach = flops / (bwd_ms * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "jet reverse pass, domain condition (order-2 jets)",
+            kname = f"jet_bwd_tc<{din}, {order_dom}, *>" if model.jet_engine.tc_supported(order_dom) else "jet_bwd_ffma"
+            roofline = {"bound": "tensor", "kernel": f"jet reverse pass, domain condition ({kname})",
                         "achieved": ach, "peak": peak_bf16, "unit": "TFLOP/s", "frac": ach / peak_bf16,
-                        "peak_source": peak_src,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
-                        # capture of this exact workload (profiles/r1_tc_ncu_summary.txt); null elsewhere
-                        "traffic": (14.334291e9 + 1.166608e9) if (args.workload == "poisson_2D_1C" and
-                                                                   args.engine == "auto" and
-                                                                   n_domain == 1_000_000) else None,
-                        "traffic_unit": "bytes per launch",
-                        "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms,
+                        "peak_source": peak_src + " (bf16 dense; the TF32 matmul peak measured in this run is "
+                                                  "tf32_matmul_peak_measured)",
+                        "traffic": ncu_traffic(args.workload, n_domain, "bwd"),
+                        "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum from the "
+                                        "committed ncu capture (profiles/r2_ncu_traffic.json); null = not captured",
+                        # N * J * 4 * P_w with J of the reference formulation (value, d first, d second
+                        # derivatives); in Laplace mode the kernels carry J_exec channels for the same result
+                        "algorithmic_flops_per_launch": flops, "channels_reference": J_ref,
+                        "channels_executed": J_exec, "executed_flops_per_launch": n_domain * J_exec * 4 * Pw,
+                        "avg_launch_ms": bwd_ms,
                         "tf32_matmul_peak_measured": tf32_peak,
                         "frac_of_tf32_peak": (ach / tf32_peak) if tf32_peak else None,
-                        # memory view of the same two kernels: the pre-activation jet stash is the algorithmic
-                        # HBM traffic (written once by the forward pass, read once by the reverse pass)
-                        "stash_bytes_per_launch": stash_bytes,
-                        "hbm_peak_GBps": hbm_peak,
+                        "stash_bytes_per_launch": stash_bytes, "hbm_peak_GBps": hbm_peak,
                         "hbm_frac_reverse": stash_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak,
-                        "hbm_frac_forward": (stash_bytes / (sum(fwd) / len(fwd) * 1e-3) / 1e9 / hbm_peak) if fwd else None,
-                        "fwd_avg_launch_ms": (sum(fwd) / len(fwd)) if fwd else None,
-                        "fwd_achieved": (n_domain * J * 2 * Pw / (sum(fwd) / len(fwd) * 1e-3) / 1e12) if fwd else None}
+                        "hbm_frac_forward": (stash_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak) if fwd_ms else None,
+                        "fwd_avg_launch_ms": fwd_ms, "residual_program_avg_launch_ms": res_ms,
+                        "fwd_achieved": (n_domain * J_ref * 2 * Pw / (fwd_ms * 1e-3) / 1e12) if fwd_ms else None,
+                        "fwd_traffic": ncu_traffic(args.workload, n_domain, "fwd"),
+                        "our_kernels_ms_per_step_unfused_launches": kernel_ms_per_step}
         step_flops = 0
-        for i, (f, _) in enumerate(spec):
-            plan = conds[i].plan_for(model)
-            for order in plan.orders:
+        for i in range(len(spec)):
+            if programs[i] is not None:
+                orders = [min(b.order, 2) for b in programs[i].blocks]
+            else:
+                orders = conds[i].plan_for(model).orders
+            for order in orders:
                 step_flops += len(dev_pts[i]) * (1 + order * din) * 6 * Pw
         line = {
             "metric": "collocation points/sec per full train step", "value": global_points / (ms * 1e-3),
@@ -384,6 +459,13 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {kind} {kw}, {n_domain} domain + {len(spec) - 1}x{n_bound} "
                                    f"boundary points per GPU, calc_loss=mean, Adam(1e-3)+ExponentialLR",
                        "engine": args.engine, "points_per_gpu": local_points, "regularization": args.regularization,
+                       "step_path": ("fused step (traced residual programs)" if fs is not None else
+                                     "eager jet path (autograd + torch element-wise residuals)"),
+                       "cuda_graphs": bool(fs is not None and not args.no_graphs), "graph_replays": graph_replays,
+                       "traced_conditions": sum(p is not None for p in programs), "conditions": len(programs),
+                       "untraced_reasons": [c.trace_note for c in conds if c.trace_note],
+                       "domain_jet_order": order_dom, "domain_channels": J_exec,
+                       "laplace_mode": order_dom == 3,
                        "l2": "per-step working set (pre-activation stash, GBs) exceeds L2; no explicit flush",
                        "algorithmic_tflop_per_step_per_gpu": step_flops / 1e12},
             "clocks": clock_info,
@@ -396,26 +478,54 @@ def run_ours(args):
         if world == 1 and not args.no_baselines:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            nd, nb = (256, 256) if args.workload == "regression_1D" else (20_000, 1_000)
-            v, cms, npts, _ = reference_cpu_run(args.workload, 8, 2, nd, nb)
+            nd, nb = cpu_sample_sizes(args.workload)
+            c_steps, c_warm = 6, 2
+            v, cms, npts, _ = reference_cpu_run(args.workload, c_steps, c_warm, nd, nb)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "ms_per_step": cms,
                                     "sample": f"{nd} domain + {nb}/boundary points per step ({npts} total), "
-                                              "10 steps, nested torch.autograd on CPU"}
+                                              f"{c_steps} timed steps after {c_warm} warm-up, nested torch.autograd "
+                                              "with TorchScript-fused activations on CPU"}
             # the reference's own torch-CUDA autograd step on this GPU: the SAME point counts as our arm when
-            # its nested-autograd graph fits in memory, else a bounded sample
+            # its nested-autograd graph fits in memory, else a bounded sample; with the reference's TorchScript
+            # activations (its real code path) and, for comparison, with plain eager activations
             sizes = [(256, 256)] if args.workload == "regression_1D" else [(n_domain, n_bound), (100_000, 5_000)]
-            for nd2, nb2 in sizes:
-                try:
-                    torch.cuda.empty_cache()
-                    v2, cms2, npts2, _ = reference_cpu_run(args.workload, 3, 2, nd2, nb2, device="cuda")
-                    line["ref_torch_cuda"] = {"value": v2, "unit": "points/s", "ms_per_step": cms2,
-                                              "speedup_of_this_arm": line["value"] / v2,
-                                              "sample": f"{nd2} domain + {nb2}/boundary points ({npts2} total), "
-                                                        "nested torch.autograd fp32 (TF32 off) on the same B200"}
-                    break
-                except Exception as ex:  # out of memory etc.
-                    line["ref_torch_cuda"] = {"unavailable": str(ex)[:200]}
+            for label, scripted in (("ref_torch_cuda", True), ("ref_torch_cuda_eager_activations", False)):
+                for nd2, nb2 in sizes:
+                    try:
+                        torch.cuda.empty_cache()
+                        v2, cms2, npts2, _ = reference_cpu_run(args.workload, 3, 3, nd2, nb2, device="cuda",
+                                                               scripted=scripted)
+                        line[label] = {"value": v2, "unit": "points/s", "ms_per_step": cms2,
+                                       "speedup_of_this_arm": line["value"] / v2,
+                                       "sample": f"{nd2} domain + {nb2}/boundary points ({npts2} total), nested "
+                                                 "torch.autograd fp32 (TF32 off) on the same B200, activations "
+                                                 + ("@torch.jit.script as in the reference" if scripted else "eager")}
+                        break
+                    except Exception as ex:  # out of memory etc.
+                        line[label] = {"unavailable": str(ex)[:200]}
+            # parity at the bench's full size: step-0 loss and flat parameter gradient, this arm vs the reference
+            # algorithm (fp32 and, if it fits, fp64) on the same points and weights
+            if ours0 is not None:
+                par = {"points": local_points}
+                for dt_name, dt in (("fp32", torch.float32), ("fp64", torch.float64)):
+                    try:
+                        torch.cuda.empty_cache()
+                        AR, rm, fns, rpts = reference_model_and_points(
+                            args.workload, n_domain, n_bound, "cuda", sd0, host_np)
+                        rm = rm.to(dt)
+                        rpts = [p.detach().to(dt).requires_grad_() for p in rpts]
+                        rt, _ = AR.mean_loss(rm, fns, rpts)
+                        rt.backward()
+                        rg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                                        for p in rm.parameters()]).double()
+                        og = ours0[1].double()
+                        par[f"loss_rel_err_vs_{dt_name}"] = abs(ours0[0] - float(rt)) / abs(float(rt))
+                        par[f"grad_rel_err_vs_{dt_name}"] = float((og - rg).abs().max() / rg.abs().max())
+                        del rm, rpts, rt, rg
+                    except Exception as ex:
+                        par[f"{dt_name}_unavailable"] = str(ex)[:120]
+                line["parity_full_size"] = par
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -432,6 +542,9 @@ def main():
     ap.add_argument("--domain-points", type=int, default=0)
     ap.add_argument("--bound-points", type=int, default=0)
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="A/B: eager jet path (autograd + torch residual algebra)")
+    ap.add_argument("--no-graphs", action="store_true", help="A/B: fused step launched kernel by kernel")
+    ap.add_argument("--no-laplace", action="store_true", help="A/B: keep d second-order channels (no Laplace mode)")
     ap.add_argument("--regularization", default="none", choices=["none", "gradient", "normal", "pointwise"],
                     help="calc_loss: 'none' = \"mean\" (the BASELINE metric); 'gradient' = GradientLosses(0.9), "
                          "the shipped default of poisson_2D_1C (secondary number)")

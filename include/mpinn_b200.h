@@ -13,6 +13,11 @@
  *
  * Jet channels of a network output, per point:  0 = value, 1..d = d/dx_i, d+1..2d = d2/dx_i^2;
  * J = 1 + order*d for order in {0,1,2}.
+ * order 3 (MPINN_ORDER_LAPLACE) carries the value, the d first derivatives and ONE second-order channel
+ * L = sum_i c_i d2/dx_i^2 with caller-supplied constant weights c (J = d + 2): what a residual needs when it
+ * uses second derivatives only through a Laplacian / a single u_xx (reference examples/poisson_2D_1C/problem.py:24-37,
+ * examples/burgers_1D/problem.py:15-18).  It is exact, not an approximation: L obeys its own layer recursion
+ *   a_L = s''(z) sum_i c_i z_i^2 + s'(z) z_L.
  */
 #ifndef MPINN_B200_H
 #define MPINN_B200_H
@@ -24,13 +29,14 @@
 extern "C" {
 #endif
 
-#define MPINN_ABI_VERSION 1
+#define MPINN_ABI_VERSION 2
 #define MPINN_MAX_OPS 64
 
 enum { MPINN_OP_LINEAR = 0, MPINN_OP_FOURIER = 1 };
 enum { MPINN_ACT_NONE = 0, MPINN_ACT_SINE = 1, MPINN_ACT_GELU = 2 };
 enum { MPINN_FLAG_SAVE_SKIP = 1, MPINN_FLAG_ADD_SKIP = 2 };
 enum { MPINN_ENGINE_AUTO = 0, MPINN_ENGINE_FFMA = 1, MPINN_ENGINE_TCGEN05 = 2 };
+#define MPINN_ORDER_LAPLACE 3
 
 /* One layer of the network "program" (host struct, passed by pointer to host memory).
  *   LINEAR : z = W h + b (+ skip), a = act(z); W is [out_dim,in_dim] at params+w_off, b at params+b_off
@@ -65,10 +71,11 @@ int mpinn_pack_params(const mpinn_op_t* ops_host, int n_ops, const float* params
  *   residual_neural_network.py:114-126, fourier_features.py:73-76, condition/diff.py:25-47.
  *   x    [n,d]      collocation points
  *   out  [J,n,o]    jets of the o network outputs (o = out_dim of the last op)
- *   stash           mpinn_stash_bytes() bytes, or NULL for a value-only/inference pass      */
+ *   stash           mpinn_stash_bytes() bytes, or NULL for a value-only/inference pass
+ *   lap_coef_host   HOST pointer to the d weights c_i of the second-order channel when order == 3, else NULL */
 int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params,
-                      const void* packed, const float* x, int64_t n, int d, int order, float* out,
-                      void* stash, int engine, void* stream);
+                      const void* packed, const float* x, int64_t n, int d, int order,
+                      const float* lap_coef_host, float* out, void* stash, int engine, void* stream);
 
 /* Reverse pass: parameter gradient of a scalar loss given dL/d(out jets).
  * Replaces `loss.backward()` through the double-backward graph (reference trainer/trainer.py:141).
@@ -78,9 +85,12 @@ int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params
  *                    `batch_loss.backward()` leaves behind), else skipped; refused for a FOURIER first op */
 int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* params,
                        const void* packed, const float* x, int64_t n, int d, int order,
-                       const float* dout, const void* stash, float* dparams, int64_t n_params,
-                       float* dx, void* workspace, size_t workspace_bytes, int engine,
+                       const float* lap_coef_host, const float* dout, const void* stash, float* dparams,
+                       int64_t n_params, float* dx, void* workspace, size_t workspace_bytes, int engine,
                        void* stream);
+
+/* 1 if `engine` (MPINN_ENGINE_*) can run this program at (d, order), else 0 (host-only query). */
+int mpinn_engine_supports(const mpinn_op_t* ops_host, int n_ops, int d, int order, int engine);
 
 /* Diagnostic: one tcgen05.mma product through the same descriptor / layout / issue helpers the jet kernels use, so
  * that the tensor-core conventions can be pinned in isolation by tests.
@@ -107,6 +117,63 @@ int mpinn_sumsq(const float* r, int64_t n, int64_t stride, float* accum, void* s
 int mpinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     int64_t n, int64_t step, float lr, float beta1, float beta2, float eps,
                     float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Residual programs.  The user's residual callable (reference examples/<name>/problem.py, evaluated per
+ * batch by Condition.get_residual, reference condition/condition.py:62-71) is traced once into a
+ * straight-line SSA program over per-point scalars: instruction i defines register i.
+ *   CONST a        r = consts[a]                       LOADX a      r = x[n][a]
+ *   LOADJ a b      r = jets[a][j][n][k], b = j*o + k   (block a = the a-th model(arg) call)
+ *   ADD SUB MUL DIV a b ;  NEG SIN COS EXP TANH RELU ABS SQRT LOG a ;  POWI a b (integer exponent b) ;
+ *   POWF a b (exponent = constant register b)
+ * jet_reg[a][j*o+k] is the register that loads that channel, or -1 if the residual does not read it. */
+enum {
+  MPINN_RP_CONST = 0, MPINN_RP_LOADX = 1, MPINN_RP_LOADJ = 2, MPINN_RP_LOADD = 3,
+  MPINN_RP_ADD = 10, MPINN_RP_SUB = 11, MPINN_RP_MUL = 12, MPINN_RP_DIV = 13,
+  MPINN_RP_NEG = 20, MPINN_RP_SIN = 21, MPINN_RP_COS = 22, MPINN_RP_EXP = 23, MPINN_RP_TANH = 24,
+  MPINN_RP_RELU = 25, MPINN_RP_ABS = 26, MPINN_RP_SQRT = 27, MPINN_RP_LOG = 28,
+  MPINN_RP_POWI = 30, MPINN_RP_POWF = 31
+};
+#define MPINN_RP_MAX_INSTR 192
+#define MPINN_RP_MAX_CONST 64
+#define MPINN_RP_MAX_OUT 8
+#define MPINN_RP_MAX_BLOCKS 4
+#define MPINN_RP_MAX_JO 32
+
+typedef struct mpinn_rinstr { int16_t op, a, b, c; } mpinn_rinstr_t;
+typedef struct mpinn_rprog {
+  int32_t n_instr, n_const, n_out, n_blocks, d, n_data, reserved0, reserved1;
+  int32_t block_J[MPINN_RP_MAX_BLOCKS], block_o[MPINN_RP_MAX_BLOCKS];
+  int16_t out_reg[MPINN_RP_MAX_OUT];
+  int16_t jet_reg[MPINN_RP_MAX_BLOCKS][MPINN_RP_MAX_JO];
+  mpinn_rinstr_t instr[MPINN_RP_MAX_INSTR];
+  float consts[MPINN_RP_MAX_CONST];
+} mpinn_rprog_t;
+
+/* Evaluate the residual components r_k[n] of one condition at n points and, in the same launch,
+ *   sums[k]    += sum_n r_k[n]^2                                (replaces torch.sum(r**2), reference PINN/PINN.py:123)
+ *   djets[a]    = d/d(jets[a]) of  sum_k weights[k] * sum_n r_k[n]^2   (the seeds of mpinn_jet_backward; replaces the
+ *                 autograd graph between the residual list and the network outputs)
+ *   values[k][n] = r_k[n]                                       (optional: what Condition.get_residual returns;
+ *                                                                 values_point_major != 0 stores values[n][k] instead)
+ * prog_host and the two pointer tables are HOST memory; jets[a] / djets[a] are device [J_a, n, o_a] blocks.
+ * djets, weights (device [n_out]), sums (device [n_out]) and values may each be NULL.  A program without model
+ * calls (n_blocks == 0, jets_host NULL) is allowed: it maps point columns to point columns, which is how the points
+ * of a second model call such as model(arg + 1) (reference examples/regression_1D/problem.py:17-35) or a shifted
+ * boundary (examples/burgers_1D/problem.py:20-25) are produced on the device. */
+int mpinn_residual_program(const mpinn_rprog_t* prog_host, const float* x, int64_t n,
+                           const float* const* jets_host, float* const* djets_host,
+                           const float* weights, float* sums, float* values, int values_point_major,
+                           void* stream);
+
+/* Adam with its scalar state on the device, so that a captured CUDA graph of the train step can be replayed
+ * while the learning rate and the step count change: state = {lr, step, step_size, sqrt(1 - beta2^step)}.
+ * mpinn_adam_tick increments state[1] and refreshes state[2..3] (bias corrections in double precision);
+ * mpinn_adam_step_dev then applies the same update as mpinn_adam_step.  The caller writes state[0] (lr). */
+int mpinn_adam_tick(float* state, float beta1, float beta2, void* stream);
+int mpinn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* state, float beta1, float beta2, float eps, float grad_scale,
+                        void* stream);
 
 #ifdef __cplusplus
 }

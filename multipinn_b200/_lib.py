@@ -14,11 +14,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmpinn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OP_LINEAR, OP_FOURIER = 0, 1
 ACT_NONE, ACT_SINE, ACT_GELU = 0, 1, 2
 FLAG_SAVE_SKIP, FLAG_ADD_SKIP = 1, 2
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05 = 0, 1, 2
+ORDER_LAPLACE = 3
 
 # every symbol include/mpinn_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -29,10 +30,16 @@ SIGNATURES = {
     "mpinn_packed_bytes": (c_size_t, [c_void_p, c_int]),
     "mpinn_pack_params": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mpinn_jet_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                  c_int, c_void_p, c_void_p, c_int, c_void_p]),
+                                  c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mpinn_jet_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                   c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_size_t, c_int, c_void_p]),
+    "mpinn_engine_supports": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
+    "mpinn_residual_program": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p]),
+    "mpinn_adam_tick": (c_int, [c_void_p, c_float, c_float, c_void_p]),
+    "mpinn_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float,
+                                    c_float, c_float, c_float, c_void_p]),
     "mpinn_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpinn_debug_counters": (c_int, [c_void_p, c_int]),
     "mpinn_sumsq": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

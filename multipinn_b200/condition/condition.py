@@ -14,6 +14,7 @@ from typing import Callable, List, Union
 
 import torch
 
+from .. import trace as _trace
 from ..jet import ResidualPlan, UnsupportedDerivative, use_plan
 
 
@@ -27,6 +28,8 @@ class Condition:
         self.batch_points = None
         self.output_len = None
         self._plans = weakref.WeakKeyDictionary()
+        self._programs = weakref.WeakKeyDictionary()   # model -> traced ResidualProgram, or None (eager path)
+        self.trace_note = None                         # why the last trace attempt fell back, for diagnostics
 
     # -- jet-order bookkeeping -------------------------------------------------------------
     def plan_for(self, model) -> ResidualPlan:
@@ -38,6 +41,56 @@ class Condition:
             plan = ResidualPlan()
             self._plans[model] = plan
         return plan
+
+    # -- traced residual programs (fused train step) ------------------------------------------
+    def program_for(self, model):
+        """The device program this condition's residual was traced into for ``model``, or None."""
+        try:
+            return self._programs.get(model)
+        except TypeError:
+            return None
+
+    def _trace(self, model, probe: torch.Tensor) -> None:
+        """Try to record the residual as a device program and check it against the eager residual at a few
+        points of the bounding box.  Any failure leaves the condition on the eager jet path."""
+        from ..neural_network.base import JetModule
+        self.trace_note = None
+        if not isinstance(model, JetModule) or type(self).get_residual is not Condition.get_residual:
+            return
+        try:
+            self._programs[model] = None
+        except TypeError:
+            return
+        try:
+            prog = _trace.trace_residual(self.function, model, model.jet_engine.d, probe)
+            self._check_program(model, prog, probe)
+        except (_trace.TraceError, UnsupportedDerivative) as e:
+            self.trace_note = f"{type(e).__name__}: {e}"
+            return
+        except Exception as e:  # user code doing something the symbolic columns do not support
+            self.trace_note = f"{type(e).__name__}: {e}"
+            return
+        self._programs[model] = prog
+
+    def _check_program(self, model, prog, probe: torch.Tensor, n: int = 8) -> None:
+        from ..fused import ConditionRunner
+        low = torch.as_tensor(self.geometry.bbox[0], dtype=torch.float32, device=probe.device)
+        high = torch.as_tensor(self.geometry.bbox[1], dtype=torch.float32, device=probe.device)
+        gen = torch.Generator(device="cpu").manual_seed(1234)
+        u = torch.rand((n, low.numel()), generator=gen, dtype=torch.float32).to(probe.device)
+        x = (low + (high - low) * u).contiguous()
+        with torch.no_grad():
+            got = ConditionRunner(self, prog, model.jet_engine).residual_values(x)
+        want = self.get_residual_fn(model)(x.clone().requires_grad_())
+        if len(want) != got.shape[0]:
+            raise _trace.TraceError("traced program has a different number of components")
+        for k, w in enumerate(want):
+            w = w.detach().reshape(-1).to(got.dtype)
+            scale = float(w.abs().max()) + 1e-6
+            if not bool(((got[k] - w).abs() <= 2e-3 * scale + 1e-5).all()):
+                raise _trace.TraceError(
+                    f"traced program disagrees with the eager residual on component {k} "
+                    f"(max diff {float((got[k] - w).abs().max()):.3e}, scale {scale:.3e})")
 
     def _call(self, model, *args):
         with use_plan(self.plan_for(model)):
@@ -74,7 +127,8 @@ class Condition:
         """Evaluate the residual once at the bbox centre: sets ``output_len`` (as the reference does)
         and, as a side effect, fills the jet-order plan and validates that the residual only uses
         derivatives the jet path provides."""
-        residuals = self.get_residual_fn(model)(self._probe_point(model))
+        probe = self._probe_point(model)
+        residuals = self.get_residual_fn(model)(probe)
         self.output_len = len(residuals)
         for k, r in enumerate(residuals):
             if isinstance(r, torch.Tensor) and bool(torch.isnan(r).any()):
@@ -82,6 +136,7 @@ class Condition:
                     f"residual component {k} of {getattr(self.function, '__name__', self.function)} is NaN at "
                     "the probe point: it most likely uses a mixed second derivative, which the fused jet "
                     "path does not compute (only d2/dx_i^2).")
+        self._trace(model, probe)
 
 
 class ConditionExtra(Condition):

@@ -30,19 +30,28 @@ int64_t tc_block_floats(int width);
 cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* packed,
                            cudaStream_t stream);
 cudaError_t read_tc_debug(long long* out, int n);
+// residual.cu
+cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
+                            float* const* djets, const float* weights, float* sums, float* values,
+                            int values_point_major, int sm_count, cudaStream_t stream);
+cudaError_t launch_adam_tick(float* state, float beta1, float beta2, cudaStream_t stream);
+cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* state,
+                            float beta1, float beta2, float eps, float grad_scale, cudaStream_t stream);
 
 // Translate the host program into the device description: padded dims, packed-buffer offsets,
 // stash planes.  Returns an error string or nullptr.
-static const char* build_prog(const mpinn_op_t* ops, int n_ops, int d, int order, DevProg* out) {
+static const char* build_prog(const mpinn_op_t* ops, int n_ops, int d, int order, DevProg* out,
+                              const float* lap_coef = nullptr) {
   if (!ops || n_ops <= 0) return "empty program";
   if (n_ops > kMaxOps) return "program has more than MPINN_MAX_OPS ops";
   if (d < 1 || d > 3) return "input dimension must be 1, 2 or 3";
-  if (order < 0 || order > 2) return "jet order must be 0, 1 or 2";
+  if (order < 0 || order > 3) return "jet order must be 0, 1, 2 or 3 (MPINN_ORDER_LAPLACE)";
   DevProg& p = *out;
   memset(&p, 0, sizeof(p));
   p.n_ops = n_ops;
   p.d = d;
-  const int J = 1 + order * d;
+  for (int i = 0; i < d; ++i) p.lap_c[i] = lap_coef ? lap_coef[i] : 1.0f;
+  const int J = jet_count(d, order);
   int cur_w = d, max_w = round_up(d, 8), planes = 0;
   int64_t pk = 0;
   for (int l = 0; l < n_ops; ++l) {
@@ -251,10 +260,11 @@ static bool use_tc(const DevProg& prog, int d, int order, int engine, bool backw
 }
 
 int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, const void* packed,
-                      const float* x, int64_t n, int d, int order, float* out, void* stash,
-                      int engine, void* stream) {
+                      const float* x, int64_t n, int d, int order, const float* lap_coef_host, float* out,
+                      void* stash, int engine, void* stream) {
   DevProg prog;
-  const char* err = build_prog(ops, n_ops, d, order, &prog);
+  if (order == MPINN_ORDER_LAPLACE && !lap_coef_host) return fail("order 3 needs lap_coef_host");
+  const char* err = build_prog(ops, n_ops, d, order, &prog, lap_coef_host);
   if (err) return fail(err);
   if (ops[0].in_dim != d) return fail("first op in_dim must equal d");
   if (n <= 0) return 0;
@@ -264,12 +274,15 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
   const int64_t n_pad = round_up64(n, 128);
-  int rc;
-  if (stash != nullptr && use_tc(prog, d, order, engine, false, &rc)) {
+  int rc = 0;
+  const bool tc = use_tc(prog, d, order, engine, false, &rc);
+  if (rc) return rc;
+  if (tc && stash == nullptr && engine == MPINN_ENGINE_TCGEN05)
+    return fail("the tcgen05 engine needs a stash buffer (pass mpinn_stash_bytes() bytes, also for inference)");
+  if (tc && stash != nullptr) {
     e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
                       info.sm_count, (cudaStream_t)stream);
   } else {
-    if (rc) return rc;
     e = launch_fwd_ffma(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash,
                         n_pad, info.sm_count, info.smem_optin, (cudaStream_t)stream);
   }
@@ -280,11 +293,12 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
 }
 
 int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, const void* packed,
-                       const float* x, int64_t n, int d, int order, const float* dout,
-                       const void* stash, float* dparams, int64_t n_params, float* dx,
+                       const float* x, int64_t n, int d, int order, const float* lap_coef_host,
+                       const float* dout, const void* stash, float* dparams, int64_t n_params, float* dx,
                        void* workspace, size_t workspace_bytes, int engine, void* stream) {
   DevProg prog;
-  const char* err = build_prog(ops, n_ops, d, order, &prog);
+  if (order == MPINN_ORDER_LAPLACE && !lap_coef_host) return fail("order 3 needs lap_coef_host");
+  const char* err = build_prog(ops, n_ops, d, order, &prog, lap_coef_host);
   if (err) return fail(err);
   if (n <= 0) return 0;
   if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
@@ -302,13 +316,14 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
   const int64_t n_pad = round_up64(n, 128);
-  int rc;
-  if (use_tc(prog, d, order, engine, true, &rc)) {
+  int rc = 0;
+  const bool tc = use_tc(prog, d, order, engine, true, &rc);
+  if (rc) return rc;
+  if (tc) {
     e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
                       n_pad, (float*)workspace, slabs, n_params, dparams, dx, skip_scratch, info.sm_count,
                       (cudaStream_t)stream);
   } else {
-    if (rc) return rc;
     e = launch_bwd_ffma(prog, params, (const float*)packed, x, n, d, order, dout,
                         (const float*)stash, n_pad, (float*)workspace, slabs, n_params, dparams, dx,
                         info.sm_count, info.smem_optin, (cudaStream_t)stream);
@@ -316,6 +331,78 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (e == cudaErrorInvalidConfiguration)
     return fail("layer widths too large for the shared-memory budget of this engine");
   if (e != cudaSuccess) return fail_cuda("jet_backward", e);
+  return 0;
+}
+
+int mpinn_engine_supports(const mpinn_op_t* ops, int n_ops, int d, int order, int engine) {
+  DevProg prog;
+  if (build_prog(ops, n_ops, d, order, &prog)) return 0;
+  if (engine == MPINN_ENGINE_TCGEN05) return tc_forward_supported(prog, d, order) ? 1 : 0;
+  return 1;   // the FP32-FMA engine runs every valid program (shared-memory budget is checked at launch)
+}
+
+int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n, const float* const* jets,
+                           float* const* djets, const float* weights, float* sums, float* values,
+                           int values_point_major, void* stream) {
+  if (!prog || !x) return fail("null pointer");
+  if (prog->n_blocks > 0 && !jets) return fail("residual program: null jet table");
+  if (prog->n_blocks == 0 && djets) return fail("residual program: seeds requested without model calls");
+  if (n <= 0) return 0;
+  if (prog->n_instr < 1 || prog->n_instr > MPINN_RP_MAX_INSTR) return fail("residual program: bad instruction count");
+  if (prog->n_out < 1 || prog->n_out > MPINN_RP_MAX_OUT) return fail("residual program: bad output count");
+  if (prog->n_blocks < 0 || prog->n_blocks > MPINN_RP_MAX_BLOCKS) return fail("residual program: bad block count");
+  if (prog->n_const < 0 || prog->n_const > MPINN_RP_MAX_CONST) return fail("residual program: bad constant count");
+  if (prog->d < 1 || prog->d > 3) return fail("residual program: bad input dimension");
+  for (int b = 0; b < prog->n_blocks; ++b) {
+    if (!jets[b]) return fail("residual program: null jet block");
+    if (prog->block_o[b] < 1 || prog->block_J[b] < 1 || prog->block_J[b] * prog->block_o[b] > MPINN_RP_MAX_JO)
+      return fail("residual program: bad block shape");
+  }
+  // every operand must name an earlier register (SSA) and every leaf an existing column
+  for (int i = 0; i < prog->n_instr; ++i) {
+    const mpinn_rinstr_t& in = prog->instr[i];
+    bool ok = true;
+    switch (in.op) {
+      case MPINN_RP_CONST: ok = in.a >= 0 && in.a < prog->n_const; break;
+      case MPINN_RP_LOADX: ok = in.a >= 0 && in.a < prog->d; break;
+      case MPINN_RP_LOADJ:
+        ok = in.a >= 0 && in.a < prog->n_blocks && in.b >= 0 && in.b < prog->block_J[in.a] * prog->block_o[in.a];
+        break;
+      case MPINN_RP_ADD: case MPINN_RP_SUB: case MPINN_RP_MUL: case MPINN_RP_DIV: case MPINN_RP_POWF:
+        ok = in.a >= 0 && in.a < i && in.b >= 0 && in.b < i; break;
+      case MPINN_RP_NEG: case MPINN_RP_SIN: case MPINN_RP_COS: case MPINN_RP_EXP: case MPINN_RP_TANH:
+      case MPINN_RP_RELU: case MPINN_RP_ABS: case MPINN_RP_SQRT: case MPINN_RP_LOG: case MPINN_RP_POWI:
+        ok = in.a >= 0 && in.a < i; break;
+      default: ok = false;
+    }
+    if (!ok) return fail("residual program: malformed instruction " + std::to_string(i));
+  }
+  for (int k = 0; k < prog->n_out; ++k)
+    if (prog->out_reg[k] < 0 || prog->out_reg[k] >= prog->n_instr) return fail("residual program: bad output register");
+  DeviceInfo info;
+  cudaError_t e = device_info(&info);
+  if (e != cudaSuccess) return fail_cuda("device query", e);
+  e = launch_residual(*prog, x, n, jets, djets, weights, sums, values, values_point_major, info.sm_count,
+                      (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("residual_program", e);
+  return 0;
+}
+
+int mpinn_adam_tick(float* state, float beta1, float beta2, void* stream) {
+  if (!state) return fail("null pointer");
+  cudaError_t e = launch_adam_tick(state, beta1, beta2, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("adam_tick", e);
+  return 0;
+}
+
+int mpinn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* state, float beta1, float beta2, float eps, float grad_scale,
+                        void* stream) {
+  if (n <= 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return fail("null pointer");
+  cudaError_t e = launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, grad_scale,
+                                  (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("adam_step_dev", e);
   return 0;
 }
 

@@ -30,8 +30,12 @@ struct DevOp {
 struct DevProg {
   int n_ops, max_w, has_skip, d, n_out, total_planes;
   int64_t packed_floats;
+  float lap_c[4];        // order 3 (Laplace mode): weights c_i of the single second-order channel sum_i c_i d2/dx_i2
   DevOp ops[kMaxOps];
 };
+
+// number of jet channels: order 0/1/2 -> 1 + order*d;  order 3 (MPINN_ORDER_LAPLACE) -> value, d first derivatives, L
+__host__ __device__ constexpr int jet_count(int d, int order) { return order == 3 ? d + 2 : 1 + order * d; }
 
 // internal activation code: cos z, i.e. the second half of a Fourier encoding [sin(xB), cos(xB)] seen as a
 // LINEAR(x -> xB) layer followed by an activation (reference neural_network/fourier_features.py:37-40)
@@ -128,14 +132,20 @@ __device__ __forceinline__ void act_coeffs(int act, float z, float& s0, float& s
   act_from_basis<NEED3>(act, z, P, Q, s0, s1, s2, s3);
 }
 
-// forward activation jets, in place: z[J] -> a[J]
+// forward activation jets, in place: z[J] -> a[J]   (lc = DevProg::lap_c, read in Laplace mode only)
 template <int D, int ORDER>
-__device__ __forceinline__ void act_jets(int act, float* z) {
+__device__ __forceinline__ void act_jets(int act, float* z, const float* lc) {
   if (act == MPINN_ACT_NONE) return;
   float s0, s1, s2, s3;
   act_coeffs<false>(act, z[0], s0, s1, s2, s3);
   z[0] = s0;
-  if (ORDER >= 2) {
+  if (ORDER == 3) {
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) q = fmaf(lc[i] * z[1 + i], z[1 + i], q);
+    z[1 + D] = fmaf(s2, q, s1 * z[1 + D]);
+  }
+  if (ORDER == 2) {
 #pragma unroll
     for (int i = 0; i < D; ++i) z[1 + D + i] = fmaf(s2 * z[1 + i], z[1 + i], s1 * z[1 + D + i]);
   }
@@ -147,7 +157,7 @@ __device__ __forceinline__ void act_jets(int act, float* z) {
 
 // cosine jets (Fourier encoding second half): z[J] -> cos jets
 template <int D, int ORDER>
-__device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj) {
+__device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj, const float* lc) {
   float s, c;
   sincosf(z[0], &s, &c);
   sj[0] = s;
@@ -159,7 +169,7 @@ __device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj
       cj[1 + i] = -s * z[1 + i];
     }
   }
-  if (ORDER >= 2) {
+  if (ORDER == 2) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const float zi2 = z[1 + i] * z[1 + i];
@@ -167,23 +177,45 @@ __device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj
       cj[1 + D + i] = fmaf(-c, zi2, -s * z[1 + D + i]);
     }
   }
+  if (ORDER == 3) {
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) q = fmaf(lc[i] * z[1 + i], z[1 + i], q);
+    sj[1 + D] = fmaf(-s, q, c * z[1 + D]);
+    cj[1 + D] = fmaf(-c, q, -s * z[1 + D]);
+  }
 }
 
 // reverse of act_jets: given z[J] (pre-activation jets) and ab[J] (grad wrt activation jets),
 // overwrite ab with the grad wrt z.
 template <int D, int ORDER>
-__device__ __forceinline__ void act_jets_bwd(int act, const float* z, float* ab) {
+__device__ __forceinline__ void act_jets_bwd(int act, const float* z, float* ab, const float* lc) {
   if (act == MPINN_ACT_NONE) return;
   float s0, s1, s2, s3;
   act_coeffs<(ORDER >= 2)>(act, z[0], s0, s1, s2, s3);
   float zb0 = ab[0] * s1;
+  if (ORDER == 3) {
+    // a_L = s2 q + s1 z_L with q = sum_i c_i z_i^2
+    const float aL = ab[1 + D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const float zi = z[1 + i];
+      zb0 = fmaf(ab[1 + i] * s2, zi, zb0);
+      zb0 = fmaf(aL * lc[i] * s3, zi * zi, zb0);
+      ab[1 + i] = fmaf(2.0f * lc[i] * aL * s2, zi, ab[1 + i] * s1);
+    }
+    zb0 = fmaf(aL * s2, z[1 + D], zb0);
+    ab[1 + D] = aL * s1;
+    ab[0] = zb0;
+    return;
+  }
   if (ORDER >= 1) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const float zi = z[1 + i];
       float zbi = ab[1 + i] * s1;
       zb0 = fmaf(ab[1 + i] * s2, zi, zb0);
-      if (ORDER >= 2) {
+      if (ORDER == 2) {
         const float aii = ab[1 + D + i];
         zbi = fmaf(2.0f * aii * s2, zi, zbi);
         zb0 = fmaf(aii, fmaf(s3 * zi, zi, s2 * z[1 + D + i]), zb0);

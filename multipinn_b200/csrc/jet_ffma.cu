@@ -56,7 +56,7 @@ __device__ __forceinline__ void gemm_chunk(const float* __restrict__ hin, const 
 
 template <int D, int ORDER, int TPP>
 __device__ __forceinline__ void write_input_jets(float* buf, int W, const float* xv, int p, int g, int G) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
   for (int k = g; k < D; k += G) {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -71,8 +71,8 @@ __device__ __forceinline__ void write_input_jets(float* buf, int W, const float*
 // Fourier encoding jets of the raw input: out planes [0,m) = sin, [m,2m) = cos
 template <int D, int ORDER, int TPP>
 __device__ __forceinline__ void fourier_jets(float* buf, int W, const float* __restrict__ B, int m,
-                                             const float* xv, int p, int g, int G) {
-  constexpr int J = 1 + ORDER * D;
+                                             const float* xv, int p, int g, int G, const float* lc) {
+  constexpr int J = jet_count(D, ORDER);
   for (int f = g; f < m; f += G) {
     float z[J], sj[J], cj[J];
     z[0] = 0.0f;
@@ -81,9 +81,10 @@ __device__ __forceinline__ void fourier_jets(float* buf, int W, const float* __r
       const float b = __ldg(B + i * m + f);
       z[0] = fmaf(xv[i], b, z[0]);
       if (ORDER >= 1) z[1 + i] = b;
-      if (ORDER >= 2) z[1 + D + i] = 0.0f;
+      if (ORDER == 2) z[1 + D + i] = 0.0f;
     }
-    sincos_jets<D, ORDER>(z, sj, cj);
+    if (ORDER == 3) z[1 + D] = 0.0f;
+    sincos_jets<D, ORDER>(z, sj, cj, lc);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       buf[(j * W + f) * TPP + p] = sj[j];
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreads)
 jet_fwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ params,
              const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
              float* __restrict__ out, float* __restrict__ stash, int64_t n_pad, int n_tiles) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
   constexpr int TPP = TP + 1;
   constexpr int G = kThreads / TP;
   extern __shared__ __align__(16) float smem[];
@@ -131,7 +132,7 @@ jet_fwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
       int nxt = 0;
       while (nxt == cur || nxt == skip) ++nxt;
       if (op.kind == MPINN_OP_FOURIER) {
-        fourier_jets<D, ORDER, TPP>(bufs[nxt], W, params + op.w_off, op.out_dim / 2, xv, p, g, G);
+        fourier_jets<D, ORDER, TPP>(bufs[nxt], W, params + op.w_off, op.out_dim / 2, xv, p, g, G, prog.lap_c);
         __syncthreads();
         cur = nxt;
         continue;
@@ -164,7 +165,7 @@ jet_fwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
               for (int j = 0; j < J; ++j)
                 stash[(int64_t)(op.stash_plane + j * op.out_dim + fo) * n_pad + pt] = z[j];
             }
-            act_jets<D, ORDER>(op.act, z);
+            act_jets<D, ORDER>(op.act, z, prog.lap_c);
 #pragma unroll
             for (int j = 0; j < J; ++j) hout[(j * W + fo) * TPP + p] = z[j];
           }
@@ -194,7 +195,7 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
              const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
              const float* __restrict__ dout, const float* __restrict__ stash, int64_t n_pad,
              float* __restrict__ part_all, int64_t n_params, float* __restrict__ dx, int n_tiles) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
   constexpr int TPP = TP + 1;
   constexpr int G = kThreads / TP;
   extern __shared__ __align__(16) float smem[];
@@ -245,7 +246,7 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
 #pragma unroll
             for (int j = 0; j < J; ++j)
               z[j] = __ldg(stash + (int64_t)(op.stash_plane + j * op.out_dim + f) * n_pad + pt);
-            act_jets_bwd<D, ORDER>(op.act, z, ab);
+            act_jets_bwd<D, ORDER>(op.act, z, ab, prog.lap_c);
 #pragma unroll
             for (int j = 0; j < J; ++j) bufG[(j * W + f) * TPP + p] = ab[j];
           }
@@ -261,14 +262,14 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
       } else {
         const DevOp& pv = prog.ops[l - 1];
         if (pv.kind == MPINN_OP_FOURIER) {
-          fourier_jets<D, ORDER, TPP>(bufH, W, params + pv.w_off, pv.out_dim / 2, xv, p, g, G);
+          fourier_jets<D, ORDER, TPP>(bufH, W, params + pv.w_off, pv.out_dim / 2, xv, p, g, G, prog.lap_c);
         } else {
           for (int f = g; f < pv.out_dim; f += G) {
             float z[J];
 #pragma unroll
             for (int j = 0; j < J; ++j)
               z[j] = __ldg(stash + (int64_t)(pv.stash_plane + j * pv.out_dim + f) * n_pad + pt);
-            act_jets<D, ORDER>(pv.act, z);
+            act_jets<D, ORDER>(pv.act, z, prog.lap_c);
 #pragma unroll
             for (int j = 0; j < J; ++j) bufH[(j * W + f) * TPP + p] = z[j];
           }
@@ -377,7 +378,7 @@ template <int D, int ORDER, int TP>
 static cudaError_t launch_fwd_t(const DevProg& prog, const float* params, const float* packed,
                                 const float* x, int64_t n, float* out, float* stash, int64_t n_pad,
                                 int sm_count, cudaStream_t stream) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
   const size_t smem = ffma_smem_bytes(prog, J, TP, prog.has_skip ? 3 : 2);
   auto kern = jet_fwd_ffma<D, ORDER, TP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -397,7 +398,7 @@ static cudaError_t launch_bwd_t(const DevProg& prog, const float* params, const 
                                 const float* x, int64_t n, const float* dout, const float* stash,
                                 int64_t n_pad, float* part, int max_slabs, int64_t n_params,
                                 float* dparams, float* dx, int sm_count, cudaStream_t stream) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
   const size_t smem = ffma_smem_bytes(prog, J, TP, prog.has_skip ? 4 : 3);
   auto kern = jet_bwd_ffma<D, ORDER, TP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -430,7 +431,7 @@ static int pick_tp(const DevProg& prog, int J, int n_bufs, size_t smem_limit) {
 cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const float* packed,
                             const float* x, int64_t n, int d, int order, float* out, float* stash,
                             int64_t n_pad, int sm_count, size_t smem_limit, cudaStream_t stream) {
-  const int J = 1 + order * d;
+  const int J = jet_count(d, order);
   // the reverse pass must agree on TP (the stash is TP-independent, but keep both kernels on the
   // same tiling so their smem budgets are checked together)
   const int tp = pick_tp(prog, J, prog.has_skip ? 4 : 3, smem_limit);
@@ -445,6 +446,9 @@ cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(3, 0, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 1, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 2, 32, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(1, 3, 32, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(2, 3, 32, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(3, 3, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 0, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 1, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 2, 16, launch_fwd_t) FWD_ARGS;
@@ -454,6 +458,9 @@ cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(3, 0, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 1, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 2, 16, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(1, 3, 16, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(2, 3, 16, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(3, 3, 16, launch_fwd_t) FWD_ARGS;
 #undef FWD_ARGS
   return cudaErrorInvalidValue;
 }
@@ -463,7 +470,7 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
                             const float* stash, int64_t n_pad, float* part, int max_slabs,
                             int64_t n_params, float* dparams, float* dx, int sm_count,
                             size_t smem_limit, cudaStream_t stream) {
-  const int J = 1 + order * d;
+  const int J = jet_count(d, order);
   const int tp = pick_tp(prog, J, prog.has_skip ? 4 : 3, smem_limit);
   if (tp == 0) return cudaErrorInvalidConfiguration;
 #define BWD_ARGS \
@@ -477,6 +484,9 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(3, 0, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 1, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 2, 32, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(1, 3, 32, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(2, 3, 32, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(3, 3, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 0, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 1, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 2, 16, launch_bwd_t) BWD_ARGS;
@@ -486,6 +496,9 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(3, 0, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 1, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 2, 16, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(1, 3, 16, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(2, 3, 16, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(3, 3, 16, launch_bwd_t) BWD_ARGS;
 #undef BWD_ARGS
   return cudaErrorInvalidValue;
 }

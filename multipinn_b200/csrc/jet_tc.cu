@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ params,
            const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
            float* __restrict__ out, float* __restrict__ stash, int64_t n_pad, int n_tiles) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
+  constexpr bool LAP = (ORDER == 3);   // one second-order channel  L = sum_i c_i d2/dx_i2  (channel D+1)
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -275,7 +276,8 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       auto channel = [&](auto spec_c, const int dir_rt) {
         constexpr int spec = decltype(spec_c)::value;
         constexpr int idx_ct = spec >= 0 ? spec : 0;
-        // production order: value, then (first, second) derivative per direction
+        // production order: value, then (first, second) derivative per direction; in Laplace mode value, the D
+        // first derivatives, then L (which needs all of them)
         constexpr int j_ct = (idx_ct == 0) ? 0
                              : (ORDER == 2 ? (((idx_ct - 1) & 1) ? 1 + D + ((idx_ct - 1) >> 1) : 1 + ((idx_ct - 1) >> 1))
                                            : idx_ct);
@@ -329,8 +331,15 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               s2[ff] = c2;
               a[e] = c0;
             } else if (is_first) {
-              zi_keep[ff] = z[e];
+              if (LAP) {   // zi_keep accumulates q = sum_i c_i z_i^2
+                const float cz = prog.lap_c[dir] * z[e];
+                zi_keep[ff] = (dir == 0) ? cz * z[e] : fmaf(cz, z[e], zi_keep[ff]);
+              } else {
+                zi_keep[ff] = z[e];
+              }
               a[e] = s1[ff] * z[e];
+            } else if (LAP) {
+              a[e] = fmaf(s2[ff], zi_keep[ff], s1[ff] * z[e]);
             } else {
               a[e] = fmaf(s2[ff] * zi_keep[ff], zi_keep[ff], s1[ff] * z[e]);
             }
@@ -360,7 +369,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         // blocks of the source layer that nobody needs any more
         if (S >= 1) {
           if (kind == 0) free_mask |= 1u << BLK(0);
-          else if (ORDER == 1) free_mask |= 1u << BLK(j);
+          else if (ORDER == 1 || LAP) free_mask |= 1u << BLK(j);
           else if (is_second) free_mask |= (1u << BLK(j)) | (1u << BLK(1 + dir));
         }
         const int nb = __ffs(free_mask) - 1;
@@ -431,7 +440,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           }
 #pragma unroll
           for (int j = 0; j < J; ++j) zst[(j * kTcW + f) * 128] = z[j];
-          act_jets<D, ORDER>(sv.act, z);   // (the last hidden layer is never the Fourier op)
+          act_jets<D, ORDER>(sv.act, z, prog.lap_c);   // (the last hidden layer is never the Fourier op)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (k < o) {
@@ -490,7 +499,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 // host side
 // ---------------------------------------------------------------------------------------------
 bool tc_forward_supported(const DevProg& prog, int d, int order) {
-  const int J = 1 + order * d;
+  const int J = jet_count(d, order);
   if (prog.has_skip && prog.ops[0].kind == MPINN_OP_FOURIER) return false;   // no combined kernel variant
   if (J * kTcW > 448) return false;
   if (prog.n_ops < 3) return false;
@@ -543,6 +552,7 @@ cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float*
   TC_FWD(1, 0); TC_FWD(1, 1); TC_FWD(1, 2);
   TC_FWD(2, 0); TC_FWD(2, 1); TC_FWD(2, 2);
   TC_FWD(3, 0); TC_FWD(3, 1); TC_FWD(3, 2);
+  TC_FWD(1, 3); TC_FWD(2, 3); TC_FWD(3, 3);
 #undef TC_FWD
   return cudaErrorInvalidValue;
 }

@@ -126,7 +126,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
            const float* __restrict__ dout, const float* __restrict__ stash, int64_t n_pad,
            float* __restrict__ part_all, int64_t n_params, float* __restrict__ skipbar_all,
            float* __restrict__ dx, int n_tiles) {
-  constexpr int J = 1 + ORDER * D;
+  constexpr int J = jet_count(D, ORDER);
+  constexpr bool LAP = (ORDER == 3);   // one second-order channel L = sum_i c_i d2/dx_i2 at jet index 1 + D
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
   constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
   constexpr uint32_t kT0Col = 320;  // TMEM columns caching the activation value of the layer below (J <= 5)
@@ -286,12 +287,15 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           float a[J];
           a[0] = t0[e];
           if (ORDER >= 1) {
+            float q = 0.0f;
 #pragma unroll
             for (int i = 0; i < D; ++i) {
               const float zi = __ldg(zp + ((1 + i) * kTcW + f) * 128);
               a[1 + i] = s1 * zi;
-              if (ORDER >= 2) a[1 + D + i] = fmaf(s2 * zi, zi, s1 * __ldg(zp + ((1 + D + i) * kTcW + f) * 128));
+              if (ORDER == 2) a[1 + D + i] = fmaf(s2 * zi, zi, s1 * __ldg(zp + ((1 + D + i) * kTcW + f) * 128));
+              if (LAP) q = fmaf(prog.lap_c[i] * zi, zi, q);
             }
+            if (LAP) a[1 + D] = fmaf(s2, q, s1 * __ldg(zp + ((1 + D) * kTcW + f) * 128));
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -387,9 +391,12 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         constexpr int kind = spec >= 0 ? (jet_ct == 0 ? 0 : (jet_ct <= D ? 1 : 2)) : -1 - spec;
         constexpr bool is_first = (kind == 1);
         constexpr bool is_second = (kind == 2);
-        constexpr bool two = is_first && ORDER == 2;
+        constexpr bool two = is_first && ORDER >= 2;   // this phase also consumes the second-order abar of its direction
+        constexpr bool lap2 = LAP && is_second;         // the L channel's own phase
         const int dir = spec >= 0 ? (is_first ? jet_ct - 1 : (is_second ? jet_ct - 1 - D : 0)) : dir_rt;
         const int jet = spec >= 0 ? jet_ct : (kind == 0 ? 0 : (is_first ? 1 + dir : 1 + D + dir));
+        const int sec = LAP ? 1 + D : 1 + D + dir;      // jet index of the second-order channel paired with `dir`
+        const float lcd = LAP ? prog.lap_c[dir] : 1.0f;
         const bool first_phase = spec >= 0 ? (step == 0) : first_rt;
 
         float zb0all[kFpt];                      // value-channel zbar of this phase (bias gradient)
@@ -421,8 +428,8 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int f = f0 + c * 8 + e;
-            zi_c[c][e] = is_first ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;
-            zii_c[c][e] = two ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
+            zi_c[c][e] = (is_first || lap2) ? __ldg(zl + (jet * kTcW + f) * 128) : 0.0f;   // z_i  (L phase: z_L)
+            zii_c[c][e] = (two && !LAP) ? __ldg(zl + ((1 + D + dir) * kTcW + f) * 128) : 0.0f;
           }
         };
         request_zl(0);
@@ -437,7 +444,17 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int f = f0 + c * 8 + e;
-              yi[e] = __ldg(zm + ((1 + dir) * kTcW + f) * 128);
+              if (lap2) {   // yi <- q = sum_i c_i y_i^2 over all directions
+                float q = 0.0f;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                  const float y = __ldg(zm + ((1 + i) * kTcW + f) * 128);
+                  q = fmaf(prog.lap_c[i] * y, y, q);
+                }
+                yi[e] = q;
+              } else {
+                yi[e] = __ldg(zm + ((1 + dir) * kTcW + f) * 128);
+              }
               yii[e] = is_second ? __ldg(zm + (jet * kTcW + f) * 128) : 0.0f;
             }
           }
@@ -448,13 +465,13 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           {
             float ab[8], ab2[8], zb[8];
             tmem_ld8(tmem + lane_base + jet * kTcW + f0 + c * 8, ab);
-            if (two) tmem_ld8(tmem + lane_base + (1 + D + dir) * kTcW + f0 + c * 8, ab2);
+            if (two) tmem_ld8(tmem + lane_base + sec * kTcW + f0 + c * 8, ab2);
             if (add_sb) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int f = f0 + c * 8 + e;
                 ab[e] += sb[(jet * kTcW + f) * 128];
-                if (two) ab2[e] += sb[((1 + D + dir) * kTcW + f) * 128];
+                if (two) ab2[e] += sb[(sec * kTcW + f) * 128];
               }
             }
 #pragma unroll
@@ -469,10 +486,16 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                   v = fmaf(2.0f * ab2[e] * s2[ff], zi[e], v);
                   a0 = fmaf(ab2[e], fmaf(s3[ff] * zi[e], zi[e], s2[ff] * zii[e]), a0);
                 }
+                if (LAP) {   // abar_L reaches z_i through q = sum_i c_i z_i^2
+                  const float w = lcd * ab2[e];
+                  v = fmaf(2.0f * w * s2[ff], zi[e], v);
+                  a0 = fmaf(w * s3[ff] * zi[e], zi[e], a0);
+                }
                 acc0[ff] = a0;
                 zb[e] = v;
               } else {
                 zb[e] = ab[e] * s1[ff];
+                if (lap2) acc0[ff] = fmaf(ab[e] * s2[ff], zi[e], acc0[ff]);   // s'' z_L term of the value channel
               }
             }
             if (kind == 0) {
@@ -502,7 +525,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
               for (int e = 0; e < 8; ++e) {
                 const int f = f0 + c * 8 + e;
                 const float t1 = cache[f * 128 + p], t2 = cache[(64 + f) * 128 + p];
-                av[e] = is_first ? t1 * yi[e] : fmaf(t2 * yi[e], yi[e], t1 * yii[e]);
+                av[e] = is_first ? t1 * yi[e] : (lap2 ? fmaf(t2, yi[e], t1 * yii[e]) : fmaf(t2 * yi[e], yi[e], t1 * yii[e]));
               }
             }
 #pragma unroll
@@ -637,13 +660,14 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           float abi[8], abii[8];
+          const int sec0 = LAP ? 1 + D : 1 + D + i;
           if (ORDER >= 1) tmem_ld8(tmem + lane_base + (1 + i) * kTcW + f0 + c * 8, abi);
-          if (ORDER == 2) tmem_ld8(tmem + lane_base + (1 + D + i) * kTcW + f0 + c * 8, abii);
+          if (ORDER >= 2) tmem_ld8(tmem + lane_base + sec0 * kTcW + f0 + c * 8, abii);
           if (add_sb0) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               if (ORDER >= 1) abi[e] += sb[((1 + i) * kTcW + f0 + c * 8 + e) * 128];
-              if (ORDER == 2) abii[e] += sb[((1 + D + i) * kTcW + f0 + c * 8 + e) * 128];
+              if (ORDER >= 2) abii[e] += sb[(sec0 * kTcW + f0 + c * 8 + e) * 128];
             }
           }
 #pragma unroll
@@ -658,6 +682,11 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 const float zii = __ldg(z0p + ((1 + D + i) * kTcW + f) * 128);
                 zbi = fmaf(2.0f * abii[e] * s2[e], zi, zbi);
                 zb0[c * 8 + e] = fmaf(abii[e], fmaf(s3[e] * zi, zi, s2[e] * zii), zb0[c * 8 + e]);
+              }
+              if (LAP) {   // (z_L of the first layer is identically zero: z = W x + b)
+                const float w = prog.lap_c[i] * abii[e];
+                zbi = fmaf(2.0f * w * s2[e], zi, zbi);
+                zb0[c * 8 + e] = fmaf(w * s3[e] * zi, zi, zb0[c * 8 + e]);
               }
             }
             zbd[i][c * 8 + e] = zbi;          // d z_i / d W[f][i] = 1
@@ -768,6 +797,7 @@ cudaError_t launch_bwd_tc(const DevProg& prog, const float* params, const float*
   TC_BWD(1, 0); TC_BWD(1, 1); TC_BWD(1, 2);
   TC_BWD(2, 0); TC_BWD(2, 1); TC_BWD(2, 2);
   TC_BWD(3, 0); TC_BWD(3, 1); TC_BWD(3, 2);
+  TC_BWD(1, 3); TC_BWD(2, 3); TC_BWD(3, 3);
 #undef TC_BWD
 #undef TC_BWD_ARGS
   return cudaErrorInvalidValue;

@@ -75,29 +75,76 @@ class CudaBackend:
                    "mpinn_pack_params")
         CudaBackend.gpu_launches += 1
 
-    def jet_forward(self, ops, params, packed, x, order, out, stash, engine=_lib.ENGINE_AUTO):
+    @staticmethod
+    def _lap(lap, d):
+        """Host array of the d Laplace-mode channel weights (order 3), or NULL."""
+        if lap is None:
+            return None
+        assert len(lap) == d
+        return (ctypes.c_float * d)(*[float(v) for v in lap])
+
+    def engine_supports(self, ops, d, order, engine):
+        p, k = self._ops(ops)
+        return bool(self.lib.mpinn_engine_supports(p, k, int(d), int(order), int(engine)))
+
+    def jet_forward(self, ops, params, packed, x, order, out, stash, engine=_lib.ENGINE_AUTO, lap=None):
         p, k = self._ops(ops)
         n, d = x.shape
         tok = self._timed("fwd", n, order)
+        lap_h = self._lap(lap, d)
         _lib.check(self.lib.mpinn_jet_forward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
-                                              n, d, order, self._ptr(out), self._ptr(stash), engine,
+                                              n, d, order, lap_h, self._ptr(out), self._ptr(stash), engine,
                                               self._stream()), "mpinn_jet_forward")
         self._timed_end(tok)
         CudaBackend.gpu_launches += 1
 
     def jet_backward(self, ops, params, packed, x, order, dout, stash, dparams, workspace,
-                     engine=_lib.ENGINE_AUTO, dx=None):
+                     engine=_lib.ENGINE_AUTO, dx=None, lap=None):
         p, k = self._ops(ops)
         n, d = x.shape
         tok = self._timed("bwd", n, order)
+        lap_h = self._lap(lap, d)
         _lib.check(self.lib.mpinn_jet_backward(p, k, self._ptr(params), self._ptr(packed), self._ptr(x),
-                                               n, d, order, self._ptr(dout), self._ptr(stash),
+                                               n, d, order, lap_h, self._ptr(dout), self._ptr(stash),
                                                self._ptr(dparams), dparams.numel(), self._ptr(dx),
                                                self._ptr(workspace),
                                                workspace.numel() * workspace.element_size(), engine,
                                                self._stream()), "mpinn_jet_backward")
         self._timed_end(tok)
         CudaBackend.gpu_launches += 2
+
+    def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
+                         point_major=False):
+        """One launch: residual components of a traced program at the points ``x``; ``sums[k] += sum r_k^2``,
+        ``djets[b]`` = seeds of the reverse pass for ``sum_k weights[k] sum_n r_k^2``, ``values[k, n] = r_k``
+        (``values[n, k]`` with ``point_major``)."""
+        st = prog.struct()
+        nb = len(jets)
+        jp = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in jets]) if nb else None
+        dp = None
+        if djets is not None:
+            dp = (ctypes.c_void_p * nb)(*[(t.data_ptr() if t is not None else 0) for t in djets])
+        for t in list(jets) + [t for t in (djets or []) if t is not None]:
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+        tok = self._timed("resid", x.shape[0], 0)
+        _lib.check(self.lib.mpinn_residual_program(ctypes.byref(st), self._ptr(x), x.shape[0], jp, dp,
+                                                   self._ptr(weights), self._ptr(sums), self._ptr(values),
+                                                   1 if point_major else 0, self._stream()),
+                   "mpinn_residual_program")
+        self._timed_end(tok)
+        CudaBackend.gpu_launches += 1
+
+    def adam_tick(self, state, beta1, beta2):
+        _lib.check(self.lib.mpinn_adam_tick(self._ptr(state), float(beta1), float(beta2), self._stream()),
+                   "mpinn_adam_tick")
+        CudaBackend.gpu_launches += 1
+
+    def adam_step_dev(self, p, g, m, v, state, beta1, beta2, eps, grad_scale=1.0):
+        _lib.check(self.lib.mpinn_adam_step_dev(self._ptr(p), self._ptr(g), self._ptr(m), self._ptr(v),
+                                                p.numel(), self._ptr(state), float(beta1), float(beta2),
+                                                float(eps), float(grad_scale), self._stream()),
+                   "mpinn_adam_step_dev")
+        CudaBackend.gpu_launches += 1
 
     def selftest_umma(self, mode, a, b, c):
         _lib.check(self.lib.mpinn_selftest_umma(int(mode), self._ptr(a), self._ptr(b), self._ptr(c),
@@ -158,8 +205,10 @@ class JetEngine:
         self.workspace: Optional[torch.Tensor] = None
         self.packed_valid = False
         self.managed = False  # a trainer promises to call invalidate() after each parameter update
+        self.generation = 0   # bumped by invalidate(): jet blocks of older parameter values are never reused
         self._params = []
         self._offsets = []
+        self._tc_ok = {}
 
     # ---------------------------------------------------------------- flat buffers
     def _is_flat(self) -> bool:
@@ -231,7 +280,23 @@ class JetEngine:
         self.attach_grads()
 
     def invalidate(self):
+        """Must be called after ANY in-place change of the parameters (optimizer step, ``load_state_dict``,
+        manual ``p.data.copy_``): the kernels read packed copies of the weights."""
         self.packed_valid = False
+        self.generation += 1
+
+    def n_jets(self, order: int) -> int:
+        return self.d + 2 if order == _lib.ORDER_LAPLACE else 1 + order * self.d
+
+    def tc_supported(self, order: int) -> bool:
+        """Whether the tcgen05 engine runs this program at ``order`` (cached host-side query)."""
+        ok = self._tc_ok.get(order)
+        if ok is None:
+            b = backend()
+            ok = bool(b.engine_supports(self.ops, self.d, order, _lib.ENGINE_TCGEN05)) \
+                if hasattr(b, "engine_supports") else False
+            self._tc_ok[order] = ok
+        return ok
 
     def _ensure_packed(self):
         if not (self.packed_valid and self.managed):
@@ -239,31 +304,44 @@ class JetEngine:
             self.packed_valid = True
 
     # ---------------------------------------------------------------- kernels
-    def forward(self, x: torch.Tensor, order: int, need_stash: bool):
-        """x [N,d] fp32 contiguous -> (out [J,N,o], stash or None)."""
+    def stash_floats(self, order: int, n: int) -> int:
+        return max(backend().stash_bytes(self.ops, self.d, order, n), 4) // 4
+
+    def forward(self, x: torch.Tensor, order: int, need_stash: bool, lap=None, out=None, stash=None):
+        """x [N,d] fp32 contiguous -> (out [J,N,o], stash or None).  ``order`` 3 is the Laplace mode with channel
+        weights ``lap``.  ``out`` / ``stash`` may be caller-owned buffers (static buffers of a captured step)."""
         self.ensure_flat()
         self._ensure_packed()
         b = backend()
         n, d = x.shape
-        J = 1 + order * d
-        out = torch.empty((J, n, self.n_out), dtype=torch.float32, device=x.device)
-        stash = None
-        if need_stash or (x.is_cuda and self.kernel_engine != _lib.ENGINE_FFMA):
-            # the tensor-core engine always round-trips pre-activations through this buffer (L2-hot)
-            nbytes = b.stash_bytes(self.ops, d, order, n)
-            stash = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=x.device)
-        b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine)
+        if out is None:
+            out = torch.empty((self.n_jets(order), n, self.n_out), dtype=torch.float32, device=x.device)
+        if stash is None and (need_stash or (x.is_cuda and self.kernel_engine != _lib.ENGINE_FFMA
+                                             and self.tc_supported(order))):
+            # the tensor-core engine always round-trips pre-activations through this buffer, also for a
+            # value-only pass; programs only the FP32-FMA engine runs need no stash for inference
+            stash = torch.empty(self.stash_floats(order, n), dtype=torch.float32, device=x.device)
+        b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine,
+                      **({"lap": lap} if lap is not None else {}))
         return out, stash
 
-    def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor, want_dx: bool = False):
+    def _workspace(self, device):
+        if self.workspace is None or self.workspace.device != device:
+            nbytes = backend().workspace_bytes(self.ops, self.flat.numel())
+            self.workspace = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        return self.workspace
+
+    def backward_into(self, x, order, dout, stash, dflat, lap=None, dx=None):
+        """dflat [P] += parameter gradient for dL/d(out jets) = dout (one reverse launch + slab fold)."""
+        backend().jet_backward(self.ops, self.flat.detach(), self.packed, x, order, dout, stash, dflat,
+                               self._workspace(x.device), self.kernel_engine, dx,
+                               **({"lap": lap} if lap is not None else {}))
+
+    def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor, want_dx: bool = False,
+                 lap=None):
         """Returns the flat parameter gradient [P] for dL/d(out jets) = dout -- and, with ``want_dx``, also the
         gradient w.r.t. the points [N, d] (what the reference's ``backward()`` leaves in ``points.grad``)."""
-        b = backend()
-        if self.workspace is None or self.workspace.device != x.device:
-            nbytes = b.workspace_bytes(self.ops, self.flat.numel())
-            self.workspace = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
         dflat = torch.zeros_like(self.flat_grad)
         dx = torch.empty_like(x) if want_dx else None
-        b.jet_backward(self.ops, self.flat.detach(), self.packed, x, order, dout, stash, dflat,
-                       self.workspace, self.kernel_engine, dx)
+        self.backward_into(x, order, dout, stash, dflat, lap, dx)
         return (dflat, dx) if want_dx else dflat

@@ -1,0 +1,258 @@
+"""The fused train step: for every condition ONE forward-jet launch, ONE residual-program launch (residuals,
+sum of squares, reverse-pass seeds) and ONE reverse launch that accumulates straight into the flat gradient;
+then the loss bookkeeping, Adam with device-side scalars and the operand re-pack -- captured once into CUDA
+graphs and replayed, so a step costs the host one or two graph launches instead of ~130 kernel launches and an
+autograd graph walk.
+
+Replaces, for conditions whose residual was traced (``trace.py``), the reference's
+``Trainer._train_batches`` body: ``calc_loss`` -> ``PINN.calculate_mean_loss`` / ``calculate_loss`` ->
+``batch_loss.backward()`` -> ``optimizer.step()`` (reference ``multipinn/trainer/trainer.py:119-153``,
+``multipinn/PINN/PINN.py:91-125``).  Conditions that could not be traced keep the eager jet path; the trainer
+then does not use this module at all.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from .engine import backend
+
+
+class _BlockBuffers:
+    __slots__ = ("order", "lap", "points_prog", "x", "out", "dout", "stash")
+
+
+class ConditionRunner:
+    """Static buffers and launches of one (condition, traced program) pair.  Every ``model(...)`` call of the
+    residual is one *block*: a forward-jet launch before the residual program and a reverse launch after it."""
+
+    def __init__(self, cond, prog, engine):
+        self.cond = cond
+        self.prog = prog
+        self.engine = engine
+        self.K = len(prog.outputs)
+        self.n = -1
+        self.x = None
+        self.blocks: List[_BlockBuffers] = []
+        for b, blk in enumerate(prog.blocks):
+            bb = _BlockBuffers()
+            bb.order = blk.order
+            bb.lap = blk.lap if blk.order == _lib.ORDER_LAPLACE else None
+            bb.points_prog = prog.points_program(b)
+            bb.x = bb.out = bb.dout = bb.stash = None
+            self.blocks.append(bb)
+
+    def bind(self, n: int, device) -> bool:
+        """(Re)allocate the static buffers for n points; True if they changed (a captured graph is then stale)."""
+        if n == self.n and self.x is not None and self.x.device == device:
+            return False
+        eng = self.engine
+        self.n = n
+        self.x = torch.empty((n, eng.d), dtype=torch.float32, device=device)
+        for bb in self.blocks:
+            bb.x = self.x if bb.points_prog is None else torch.empty_like(self.x)
+            bb.out = torch.empty((eng.n_jets(bb.order), n, eng.n_out), dtype=torch.float32, device=device)
+            bb.dout = torch.empty_like(bb.out)
+            bb.stash = torch.empty(eng.stash_floats(bb.order, n), dtype=torch.float32, device=device)
+        return True
+
+    def _forward_blocks(self, x, blocks, need_stash):
+        eng, be = self.engine, backend()
+        for bb in blocks:
+            if bb.points_prog is not None:   # e.g. model(arg + 1): the shifted points are produced on the device
+                be.residual_program(bb.points_prog, x, [], None, None, None, bb.x, point_major=True)
+            eng.forward(bb.x, bb.order, need_stash, lap=bb.lap, out=bb.out, stash=bb.stash)
+
+    def launch(self, weights, sums, dflat):
+        eng = self.engine
+        self._forward_blocks(self.x, self.blocks, True)
+        backend().residual_program(self.prog, self.x, [bb.out for bb in self.blocks],
+                                   [bb.dout for bb in self.blocks], weights, sums)
+        for bb in self.blocks:
+            eng.backward_into(bb.x, bb.order, bb.dout, bb.stash, dflat, lap=bb.lap)
+
+    def residual_values(self, x: torch.Tensor) -> torch.Tensor:
+        """[K, N] residual components at arbitrary points, value-only (no seeds, no reverse pass): the fast path
+        for residual-driven samplers and callbacks."""
+        eng = self.engine
+        n = x.shape[0]
+        tmp = []
+        for bb in self.blocks:
+            t = _BlockBuffers()
+            t.order, t.lap, t.points_prog = bb.order, bb.lap, bb.points_prog
+            t.x = x if bb.points_prog is None else torch.empty_like(x)
+            t.out = torch.empty((eng.n_jets(bb.order), n, eng.n_out), dtype=torch.float32, device=x.device)
+            t.stash = None
+            tmp.append(t)
+        self._forward_blocks(x, tmp, False)
+        vals = torch.empty((self.K, n), dtype=torch.float32, device=x.device)
+        backend().residual_program(self.prog, x, [t.out for t in tmp], None, None, None, vals)
+        return vals
+
+
+class FusedStep:
+    """Whole-step executor for a trainer whose conditions are all traced."""
+
+    def __init__(self, engine, conditions, programs, mode: str, flat_adam=None, use_graphs: bool = True):
+        self.engine = engine
+        self.mode = mode                 # "mean" | "legacy"
+        self.flat_adam = flat_adam
+        self.runners: List[ConditionRunner] = [ConditionRunner(c, p, engine) for c, p in zip(conditions, programs)]
+        self.K = sum(r.K for r in self.runners)
+        self.use_graphs = use_graphs
+        self._g_compute: Optional[torch.cuda.CUDAGraph] = None
+        self._g_update: Optional[torch.cuda.CUDAGraph] = None
+        self._calls = {"_g_compute": 0, "_g_update": 0}
+        self._dev = None
+        self._lr_on_device = None
+        self._scale = 1.0
+        self.graph_replays = 0
+        self._launches = {"_g_compute": 0, "_g_update": 0}   # kernels one direct run of each part launches
+
+    @staticmethod
+    def build(trainer) -> Optional["FusedStep"]:
+        """A FusedStep for ``trainer`` or None when any precondition fails (the trainer stays on the eager path)."""
+        eng = trainer._engine
+        if eng is None or eng.points_grad or trainer.num_batches < 1:
+            return None
+        from .trainer.trainer import Trainer
+        if trainer.calc_loss == Trainer.mean_calc_loss:
+            mode = "mean"
+        elif trainer.calc_loss == Trainer.sum_of_means_calc_loss:
+            mode = "legacy"
+        else:
+            return None
+        progs = []
+        for c in trainer.pinn.conditions:
+            p = c.program_for(trainer.pinn.model) if hasattr(c, "program_for") else None
+            if p is None:
+                return None
+            progs.append(p)
+        if sum(len(p.outputs) for p in progs) + 1 > eng.COMM_TAIL:
+            return None
+        return FusedStep(eng, trainer.pinn.conditions, progs, mode, trainer._flat_adam,
+                         use_graphs=getattr(trainer, "use_cuda_graphs", True))
+
+    # ------------------------------------------------------------------ buffers
+    def _bind(self, device):
+        eng = self.engine
+        eng.ensure_flat()
+        changed = device != self._dev
+        for r in self.runners:
+            changed |= r.bind(int(r.cond.batch_points.shape[0]), device)
+        if changed:
+            self._dev = device
+            self._g_compute = self._g_update = None
+            self._calls = {"_g_compute": 0, "_g_update": 0}
+            eng.attach_grads()
+            K = self.K
+            counts = []
+            for r in self.runners:
+                counts += [float(r.n)] * r.K
+            total = float(sum(r.n * r.K for r in self.runners))
+            self.sums = torch.zeros(K, dtype=torch.float32, device=device)
+            self.inv_counts = torch.tensor([1.0 / c for c in counts], dtype=torch.float32, device=device)
+            self.inv_total = 1.0 / total
+            if self.mode == "mean":      # total = sum_k sum_n r^2 / sum_k N_k   (reference PINN.py:109-125)
+                self.weights = torch.full((K,), 1.0 / total, dtype=torch.float32, device=device)
+            else:                        # total = sum_k mean_n r^2                (reference trainer.py:155-167)
+                self.weights = self.inv_counts.clone()
+            if self.flat_adam is not None:
+                self.adam_state = torch.zeros(4, dtype=torch.float32, device=device)
+                self.adam_state[1] = float(self.flat_adam.step)
+                self._lr_on_device = None
+
+    def _loss_view(self):
+        eng = self.engine
+        P = eng.flat_grad.numel()
+        return eng.comm_buffer(self.K + 1)[P:P + self.K + 1]   # [K component means, total]
+
+    # ------------------------------------------------------------------ launches
+    def _compute(self):
+        eng = self.engine
+        eng.flat_grad.zero_()
+        self.sums.zero_()
+        k0 = 0
+        for r in self.runners:
+            r.launch(self.weights[k0:k0 + r.K], self.sums[k0:k0 + r.K], eng.flat_grad)
+            k0 += r.K
+        lv = self._loss_view()
+        torch.mul(self.sums, self.inv_counts, out=lv[:self.K])
+        if self.mode == "mean":
+            torch.mul(torch.sum(self.sums), self.inv_total, out=lv[self.K])
+        else:
+            torch.sum(lv[:self.K], dim=0, out=lv[self.K])
+
+    def _update(self, grad_scale: float):
+        eng = self.engine
+        fa = self.flat_adam
+        g = fa.optimizer.param_groups[0]
+        b1, b2 = g["betas"]
+        be = backend()
+        be.adam_tick(self.adam_state, b1, b2)
+        be.adam_step_dev(eng.flat.detach(), eng.flat_grad, fa.m, fa.v, self.adam_state, b1, b2, g["eps"], grad_scale)
+        be.pack_params(eng.ops, eng.flat.detach(), eng.packed)
+
+    def _graphed(self, which: str, fn):
+        """Run ``fn`` directly twice (kernel/module warm-up), then capture it once and replay."""
+        from .engine import CudaBackend
+
+        def direct():
+            n0 = CudaBackend.gpu_launches
+            fn()
+            self._launches[which] = CudaBackend.gpu_launches - n0
+
+        if not (self.use_graphs and self._dev is not None and self._dev.type == "cuda"):
+            direct()
+            return
+        g = getattr(self, which)
+        if g is None:
+            self._calls[which] += 1
+            if self._calls[which] <= 2:
+                direct()
+                return
+            g = torch.cuda.CUDAGraph()
+            n0 = CudaBackend.gpu_launches
+            with torch.cuda.graph(g):
+                fn()
+            CudaBackend.gpu_launches = n0      # capture launches nothing
+            setattr(self, which, g)
+        g.replay()
+        self.graph_replays += 1
+        CudaBackend.gpu_launches += self._launches[which]   # the replay runs the same kernels as a direct call
+
+    # ------------------------------------------------------------------ the step
+    def compute(self):
+        """Gradient of the total loss into ``engine.flat_grad`` and the losses into the comm tail."""
+        conds = [r.cond for r in self.runners]
+        self._bind(conds[0].batch_points.device)
+        for r in self.runners:
+            r.x.copy_(r.cond.batch_points.detach(), non_blocking=True)
+        self.engine._ensure_packed()
+        self._graphed("_g_compute", self._compute)
+
+    def update(self, grad_scale: float = 1.0) -> bool:
+        """Optimizer step on the device; False if the optimizer is not the fused Adam (caller steps it)."""
+        fa = self.flat_adam
+        if fa is None:
+            return False
+        lr = float(fa.optimizer.param_groups[0]["lr"])
+        if lr != self._lr_on_device:
+            self.adam_state[0:1].fill_(lr)
+            self._lr_on_device = lr
+        if grad_scale != self._scale:   # baked into the captured launch
+            self._scale = grad_scale
+            self._g_update = None
+        self._graphed("_g_update", lambda: self._update(self._scale))
+        fa.step += 1
+        fa.mark_stepped()
+        self.engine.generation += 1      # parameters changed; operands were re-packed inside _update
+        self.engine.packed_valid = True
+        return True
+
+    def losses(self):
+        """(total_loss 0-d, component means [K]) as fresh tensors."""
+        lv = self._loss_view().clone()
+        return lv[self.K], lv[:self.K]

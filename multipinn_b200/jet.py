@@ -28,9 +28,15 @@ from typing import Dict, List, Optional
 import torch
 from torch.autograd.function import once_differentiable
 
+from . import trace as _trace
+
 
 class UnsupportedDerivative(NotImplementedError):
     pass
+
+
+def _lap_kw(lap):
+    return {"lap": lap} if lap is not None else {}
 
 
 # ----------------------------------------------------------------------------- residual plans
@@ -100,7 +106,7 @@ class jet_order:
 # ----------------------------------------------------------------------------- jet blocks
 class JetBlock:
     __slots__ = ("out_ref", "arg_ref", "arg_ptr", "n", "d", "o", "order", "engine", "plan", "plan_idx",
-                 "offset0", "__weakref__")
+                 "offset0", "generation", "grad_mode", "__weakref__")
 
     def __init__(self, out, arg, order, engine, plan, plan_idx):
         self.out_ref = weakref.ref(out)
@@ -113,6 +119,8 @@ class JetBlock:
         self.plan = plan
         self.plan_idx = plan_idx
         self.offset0 = out.storage_offset()
+        self.generation = engine.generation          # parameter version the block was computed with
+        self.grad_mode = torch.is_grad_enabled()
 
 
 _blocks: Dict[int, JetBlock] = {}
@@ -185,6 +193,8 @@ def _run_block(engine, arg: torch.Tensor, order: int, plan, plan_idx) -> torch.T
 
 def model_forward(engine, arg: torch.Tensor) -> torch.Tensor:
     """What ``nn.Module.forward`` of the mirrored network classes calls."""
+    if isinstance(arg, _trace.TMat):       # symbolic evaluation of a residual (trace.py)
+        return _trace.traced_model_call(engine, arg)
     plan = current_plan()
     if plan is not None:
         idx = plan.next_order()
@@ -228,6 +238,8 @@ def _decode(u: torch.Tensor, b: JetBlock):
 
 def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
     """``grad(u, arg)`` of the reference (condition/diff.py:25-47), served from the jet block."""
+    if _trace.is_traced(u) or _trace.is_traced(arg):
+        return _trace.traced_grad(u, arg)
     b = _lookup(u)
     if b is None and u.grad_fn is not None and arg.requires_grad:
         # Not an output of a fused jet network: a plain torch module (the families outside the accelerated
@@ -256,7 +268,8 @@ def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
         out = None
         for other in _blocks.values():  # an earlier escalation of the same call may still be alive
             if other.engine is b.engine and other.arg_ptr == b.arg_ptr and other.n == b.n \
-                    and other.order >= need and other.out_ref() is not None:
+                    and other.order >= need and other.order <= 2 and other.out_ref() is not None \
+                    and other.generation == b.engine.generation and other.grad_mode == torch.is_grad_enabled():
                 out, b = other.out_ref(), other
                 break
         if out is None:
@@ -277,4 +290,6 @@ def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
 
 def unpack(batch: torch.Tensor) -> tuple:
     """Same as the reference's ``unpack`` (condition/diff.py:4-22): columns of ``batch`` as views."""
+    if _trace.is_traced(batch):
+        return _trace.traced_unpack(batch)
     return torch.unbind(batch, dim=1)

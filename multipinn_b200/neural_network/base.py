@@ -61,6 +61,22 @@ class JetModule(nn.Module):
     def forward(self, input_tensor: torch.Tensor) -> torch.Tensor:
         return jet.model_forward(self.jet_engine, input_tensor)
 
+    # The kernels read packed copies of the weights; a trainer re-packs after its own updates, every other
+    # in-place change of the parameters has to invalidate them.
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        eng = self.__dict__.get("_jet_engine")
+        if eng is not None:
+            eng.invalidate()
+        return res
+
+    def _apply(self, fn, *args, **kwargs):
+        res = super()._apply(fn, *args, **kwargs)
+        eng = self.__dict__.get("_jet_engine")
+        if eng is not None:
+            eng.invalidate()
+        return res
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_jet_engine", None)  # device buffers are rebuilt lazily after unpickling

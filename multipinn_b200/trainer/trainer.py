@@ -21,6 +21,7 @@ import torch.distributed as dist
 
 from .. import jet
 from ..engine import backend
+from ..fused import FusedStep
 from ..neural_network.base import JetModule
 from ..PINN import PINN
 
@@ -35,6 +36,7 @@ class _FlatAdam:
         self.m = torch.zeros_like(engine.flat_grad)
         self.v = torch.zeros_like(engine.flat_grad)
         self.step = 0
+        self._step_t = torch.tensor(0.0)   # ONE host tensor shared by every parameter's state["step"]
         for p, off in zip(engine._params, engine._offsets):
             st = optimizer.state.get(p)
             if st:  # resume from an existing torch state
@@ -52,15 +54,24 @@ class _FlatAdam:
                 g.get("capturable") or g.get("differentiable"):
             return False
         engine.ensure_flat()
+        # the reverse kernels produce gradients for every layer and the flat update steps the whole buffer, so a
+        # model with frozen layers must go through torch.optim.Adam (which skips parameters without .grad);
+        # a frozen Fourier matrix is fine: the fused reverse pass leaves its gradient slot at zero
+        ops = engine.ops
+        fourier_w = int(ops[0, 3]) if int(ops[0, 0]) == 1 else -1
+        for p, off in zip(engine._params, engine._offsets):
+            if not p.requires_grad and off != fourier_w:
+                return False
         return {id(p) for p in g["params"]} == {id(p) for p in engine._params}
 
     def _publish(self):
+        self._step_t.fill_(float(self.step))
         for p, off in zip(self.engine._params, self.engine._offsets):
             if not p.requires_grad:
                 continue
             n = p.numel()
             self.optimizer.state[p] = {
-                "step": torch.tensor(float(self.step)),
+                "step": self._step_t,
                 "exp_avg": self.m[off:off + n].view(p.shape),
                 "exp_avg_sq": self.v[off:off + n].view(p.shape),
             }
@@ -71,10 +82,10 @@ class _FlatAdam:
         b1, b2 = g["betas"]
         backend().adam_step(self.engine.flat.detach(), self.engine.flat_grad, self.m, self.v, self.step,
                             g["lr"], b1, b2, g["eps"], grad_scale)
-        for p in self.engine._params:
-            st = self.optimizer.state.get(p)
-            if st is not None:
-                st["step"].fill_(float(self.step))
+        self.mark_stepped()
+
+    def mark_stepped(self):
+        self._step_t.fill_(float(self.step))
         self.optimizer._opt_called = True  # what LRScheduler checks before its first step()
 
 
@@ -122,6 +133,11 @@ class Trainer:
         model = self.pinn.model
         self._engine = model.jet_engine if isinstance(model, JetModule) else None
         self._flat_adam = None
+        # Fused step (multipinn_b200/fused.py): used when every condition's residual was traced into a device
+        # program and the loss policy is one of the reference's two; otherwise the eager jet path below runs.
+        self.use_fused_step = True
+        self.use_cuda_graphs = True
+        self._fused = None
         if self._engine is not None:
             self._engine.ensure_flat()
             self._engine.managed = True
@@ -181,7 +197,33 @@ class Trainer:
         if self._engine is not None:
             self._engine.invalidate()
 
+    def fused_step(self):
+        """The FusedStep executor of this trainer, or None (built lazily at the first step)."""
+        if not self.use_fused_step:
+            return None
+        if self._fused is None:
+            self._fused = FusedStep.build(self) or False
+        if self._fused:
+            self._fused.use_graphs = self.use_cuda_graphs
+            return self._fused
+        return None
+
+    def _fused_batch(self, batch_index: int) -> bool:
+        """One whole optimisation step on the fused path; False if this trainer is not eligible."""
+        fs = self.fused_step()
+        if fs is None:
+            return False
+        self.current_batch = batch_index
+        self.pinn.select_batch(batch_index)
+        fs.compute()
+        if not fs.update():
+            self._optimizer_step()       # any other optimizer: gradients are in the p.grad views
+        self.total_loss, self.epoch_loss_detailed = fs.losses()
+        return True
+
     def _train_batches(self):
+        if self.num_batches == 1 and self._fused_batch(0):
+            return
         self._zero_grad()  # outside the loop: gradients accumulate over the batches
         for self.current_batch in range(self.num_batches):
             self.pinn.select_batch(self.current_batch)
@@ -211,6 +253,8 @@ class TrainerOneBatch(Trainer):
                          callbacks_organizer, mixed_training)
 
     def _train_batches(self):
+        if self._fused_batch(0):
+            return
         self.pinn.select_batch(0)
         self._zero_grad()
         batch_loss, losses = self.calc_loss(self)
@@ -241,7 +285,25 @@ class TrainerMultiGPU(Trainer):
             for p in self.pinn.model.parameters():
                 dist.broadcast(p.data, src=0)
 
+    def _fused_dp_step(self) -> bool:
+        fs = self.fused_step()
+        if fs is None:
+            return False
+        self.pinn.select_batch(0 if self.sharded_points else self.rank)
+        fs.compute()                                   # gradient + [K losses, total] in ONE flat message
+        eng = self._engine
+        msg = eng.comm_buffer(fs.K + 1)
+        dist.all_reduce(msg, op=dist.ReduceOp.SUM)
+        msg.mul_(1.0 / float(dist.get_world_size()))   # p.grad and the logged losses become means over ranks
+        if not fs.update():
+            self._optimizer_step()
+        self.total_loss, self.epoch_loss_detailed = fs.losses()
+        self._comm = None
+        return True
+
     def _train_batches(self):
+        if self._fused_dp_step():
+            return
         self._zero_grad()
         self.pinn.select_batch(0 if self.sharded_points else self.rank)
         batch_loss, losses = self.calc_loss(self)

@@ -24,6 +24,11 @@ Reference lines restated here
 
 Jet channels per point: 0 = value, 1..d = d/dx_i, d+1..2d = d2/dx_i2.
   order 0 -> J = 1, order 1 -> J = 1+d, order 2 -> J = 1+2d.
+  order 3 ("Laplace mode", include/mpinn_b200.h MPINN_ORDER_LAPLACE) -> J = d+2: value, d first derivatives and
+  the single channel L = sum_i c_i d2/dx_i2 (weights ``lap``).  L is what the reference's examples build from
+  separate nested grad() calls (e.g. examples/poisson_2D_1C/problem.py:26-29 ``u_xx + u_yy``); because the chain
+  rule for it closes on itself, a_L = s''(z) sum_i c_i z_i^2 + s'(z) z_L, it can be propagated directly.  The
+  test-suite checks it against sum_i c_i of the order-2 channels, which are pinned to the reference goldens.
 """
 from __future__ import annotations
 
@@ -48,8 +53,15 @@ FLAG_ADD_SKIP = 2
 GELU_C = 1.0 / 1.41421  # the reference divides by the literal 1.41421, not sqrt(2)
 
 
+ORDER_LAPLACE = 3
+
+
 def n_jets(d: int, order: int) -> int:
-    return 1 + order * d
+    return d + 2 if order == ORDER_LAPLACE else 1 + order * d
+
+
+def _lap(lap, d, dtype):
+    return np.ones(d, dtype=dtype) if lap is None else np.asarray(lap, dtype=dtype)
 
 
 def act_derivs(act: int, z: np.ndarray, n: int):
@@ -75,35 +87,52 @@ def act_derivs(act: int, z: np.ndarray, n: int):
     return out[: n + 1]
 
 
-def _act_jets(act, z, d, order):
+def _act_jets(act, z, d, order, lap=None):
     """z: [N,J,W] pre-activation jets -> activation jets [N,J,W]."""
     if act == ACT_NONE:
         return z.copy()
     a = np.empty_like(z)
-    ders = act_derivs(act, z[:, 0], order)
+    ders = act_derivs(act, z[:, 0], min(order, 2))
     a[:, 0] = ders[0]
+    if order == ORDER_LAPLACE:
+        c = _lap(lap, d, z.dtype)
+        q = sum(c[i] * z[:, 1 + i] ** 2 for i in range(d))
+        for i in range(d):
+            a[:, 1 + i] = ders[1] * z[:, 1 + i]
+        a[:, 1 + d] = ders[2] * q + ders[1] * z[:, 1 + d]
+        return a
     if order >= 1:
         for i in range(d):
             a[:, 1 + i] = ders[1] * z[:, 1 + i]
-    if order >= 2:
+    if order == 2:
         for i in range(d):
             a[:, 1 + d + i] = ders[2] * z[:, 1 + i] ** 2 + ders[1] * z[:, 1 + d + i]
     return a
 
 
-def _act_jets_bwd(act, z, abar, d, order):
+def _act_jets_bwd(act, z, abar, d, order, lap=None):
     """Reverse of _act_jets: given abar [N,J,W] return zbar [N,J,W]."""
     if act == ACT_NONE:
         return abar.copy()
-    ders = act_derivs(act, z[:, 0], order + 1)
+    ders = act_derivs(act, z[:, 0], min(order, 2) + 1)
     zb = np.empty_like(abar)
     zb[:, 0] = abar[:, 0] * ders[1]
+    if order == ORDER_LAPLACE:
+        c = _lap(lap, d, z.dtype)
+        aL, zL = abar[:, 1 + d], z[:, 1 + d]
+        zb[:, 1 + d] = aL * ders[1]
+        zb[:, 0] += aL * ders[2] * zL
+        for i in range(d):
+            zi = z[:, 1 + i]
+            zb[:, 1 + i] = abar[:, 1 + i] * ders[1] + 2.0 * c[i] * aL * ders[2] * zi
+            zb[:, 0] += abar[:, 1 + i] * ders[2] * zi + aL * c[i] * ders[3] * zi * zi
+        return zb
     if order >= 1:
         for i in range(d):
             zi = z[:, 1 + i]
             zb[:, 1 + i] = abar[:, 1 + i] * ders[1]
             zb[:, 0] += abar[:, 1 + i] * ders[2] * zi
-    if order >= 2:
+    if order == 2:
         for i in range(d):
             zi = z[:, 1 + i]
             zii = z[:, 1 + d + i]
@@ -125,7 +154,25 @@ def input_jets(x: np.ndarray, order: int) -> np.ndarray:
     return h
 
 
-def forward(program, params: np.ndarray, x: np.ndarray, order: int):
+def _cos_jets(z, d, order, lap=None):
+    """Jets of cos(z): cos' = -sin, cos'' = -cos."""
+    c = np.empty_like(z)
+    cz, sz = np.cos(z[:, 0]), np.sin(z[:, 0])
+    c[:, 0] = cz
+    if order >= 1:
+        for i in range(d):
+            c[:, 1 + i] = -sz * z[:, 1 + i]
+    if order == 2:
+        for i in range(d):
+            c[:, 1 + d + i] = -cz * z[:, 1 + i] ** 2 - sz * z[:, 1 + d + i]
+    if order == ORDER_LAPLACE:
+        w = _lap(lap, d, z.dtype)
+        q = sum(w[i] * z[:, 1 + i] ** 2 for i in range(d))
+        c[:, 1 + d] = -cz * q - sz * z[:, 1 + d]
+    return c
+
+
+def forward(program, params: np.ndarray, x: np.ndarray, order: int, lap=None):
     """Run the layer program.  Returns (out jets [N,J,o], cache for backward).
 
     program: int array [n_ops, 8] = kind, in_dim, out_dim, w_off, b_off, act, flags, 0
@@ -142,17 +189,8 @@ def forward(program, params: np.ndarray, x: np.ndarray, order: int):
             m = dout // 2
             B = params[w_off : w_off + din * m].reshape(din, m)
             z = h @ B  # [N,J,m]  (h is the raw input jets here)
-            s = _act_jets(ACT_SINE, z, d, order)
-            # cos jets: cos' = -sin, cos'' = -cos
-            c = np.empty_like(z)
-            cz, sz = np.cos(z[:, 0]), np.sin(z[:, 0])
-            c[:, 0] = cz
-            if order >= 1:
-                for i in range(d):
-                    c[:, 1 + i] = -sz * z[:, 1 + i]
-            if order >= 2:
-                for i in range(d):
-                    c[:, 1 + d + i] = -cz * z[:, 1 + i] ** 2 - sz * z[:, 1 + d + i]
+            s = _act_jets(ACT_SINE, z, d, order, lap)
+            c = _cos_jets(z, d, order, lap)
             cache.append(("fourier", h, z))
             h = np.concatenate([s, c], axis=2)
             continue
@@ -165,11 +203,11 @@ def forward(program, params: np.ndarray, x: np.ndarray, order: int):
         if flags & FLAG_ADD_SKIP:
             z = z + skip
         cache.append(("linear", h, z))
-        h = _act_jets(act, z, d, order)
+        h = _act_jets(act, z, d, order, lap)
     return h, cache
 
 
-def backward(program, params: np.ndarray, x: np.ndarray, order: int, cache, dout: np.ndarray):
+def backward(program, params: np.ndarray, x: np.ndarray, order: int, cache, dout: np.ndarray, lap=None):
     """Reverse pass.  dout: [N,J,o].  Returns (flat dparams, dx [N,d])."""
     program = np.asarray(program, dtype=np.int64).reshape(-1, 8)
     N, d = x.shape
@@ -183,7 +221,7 @@ def backward(program, params: np.ndarray, x: np.ndarray, order: int, cache, dout
             m = dout_ // 2
             B = params[w_off : w_off + din * m].reshape(din, m)
             sbar, cbar = hbar[:, :, :m], hbar[:, :, m:]
-            zb = _act_jets_bwd(ACT_SINE, z, sbar, d, order)
+            zb = _act_jets_bwd(ACT_SINE, z, sbar, d, order, lap)
             # cosine branch
             cz, sz = np.cos(z[:, 0]), np.sin(z[:, 0])
             zb[:, 0] += cbar[:, 0] * (-sz)
@@ -192,19 +230,28 @@ def backward(program, params: np.ndarray, x: np.ndarray, order: int, cache, dout
                     zi = z[:, 1 + i]
                     zb[:, 1 + i] += cbar[:, 1 + i] * (-sz)
                     zb[:, 0] += cbar[:, 1 + i] * (-cz) * zi
-            if order >= 2:
+            if order == 2:
                 for i in range(d):
                     zi, zii = z[:, 1 + i], z[:, 1 + d + i]
                     cii = cbar[:, 1 + d + i]
                     zb[:, 1 + d + i] += cii * (-sz)
                     zb[:, 1 + i] += 2.0 * cii * (-cz) * zi
                     zb[:, 0] += cii * (sz * zi * zi - cz * zii)
+            if order == ORDER_LAPLACE:
+                w = _lap(lap, d, z.dtype)
+                cL, zL = cbar[:, 1 + d], z[:, 1 + d]
+                zb[:, 1 + d] += cL * (-sz)
+                zb[:, 0] += cL * (-cz) * zL
+                for i in range(d):
+                    zi = z[:, 1 + i]
+                    zb[:, 1 + i] += 2.0 * w[i] * cL * (-cz) * zi
+                    zb[:, 0] += cL * w[i] * sz * zi * zi
             dB = np.einsum("njk,njm->km", h, zb)
             dparams[w_off : w_off + din * m] += dB.reshape(-1)
             hbar = zb @ B.T
             continue
         W = params[w_off : w_off + din * dout_].reshape(dout_, din)
-        zb = _act_jets_bwd(act, z, hbar, d, order)
+        zb = _act_jets_bwd(act, z, hbar, d, order, lap)
         if flags & FLAG_ADD_SKIP:
             skipbar = zb
         dW = np.einsum("njo,nji->oi", zb, h)

@@ -1,0 +1,392 @@
+"""GPU parity of the round-2 path (run on the B200 box: ``pytest -m gpu``): Laplace-mode jets, the residual-program
+kernel, the fused / CUDA-graph train step, Adam with device-side state, and the regularizers on CUDA.  Everything
+goes through the C ABI; expected values come from the reference goldens and the fp64 oracle."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import multipinn_b200 as mp
+from multipinn_b200 import _lib, engine, jet, trace
+from multipinn_b200.fused import ConditionRunner
+from oracle import autograd_ref as AR
+from oracle import jet_ref as JR
+from oracle import residual_ref as RR
+from tests import problems
+from tests.test_gpu_parity import ENGINE_IDS, ENGINES, TOL, full_model, golden_model, product_ns
+from tests.test_oracle_golden import GOLD_KW, NAMES, load, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def cuda_backend():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    old = engine._set_backend_for_tests(None)
+    jet.clear_blocks()
+    be = engine.backend()
+    assert be.name == "cuda"
+    yield be
+    engine._set_backend_for_tests(old)
+
+
+def golden_pinn(name, g, kernel_engine=_lib.ENGINE_AUTO):
+    model = golden_model(name, g, kernel_engine)
+    spec, din, dout = problems.CONFIGS[name][0](product_ns())
+    conds = []
+    for i, (fn, (lo, hi)) in enumerate(spec):
+        c = mp.Condition(fn, mp.Hypercube(lo, hi))
+        pts = torch.tensor(g[f"pts{i}"]).cuda().requires_grad_()
+        c.generator = types.SimpleNamespace(n_points=len(pts), generate=lambda cond, model, p=pts: p)
+        conds.append(c)
+    pinn = mp.PINN(model, conds)
+    pinn.update_data()
+    for c in conds:
+        c.set_batching(1)
+    return model, conds, pinn
+
+
+LAPS = {1: (1.0,), 2: (1.0, 0.25), 3: (1.0, -0.5, 2.0)}
+
+
+# ------------------------------------------------------------------------------ Laplace-mode jets
+@pytest.mark.parametrize("eng", ENGINES, ids=ENGINE_IDS)
+@pytest.mark.parametrize("name", NAMES)
+def test_laplace_mode_forward_and_reverse_match_oracle(name, eng):
+    """order 3: value, first derivatives and L = sum_i c_i d2/dx_i2 against the fp64 oracle, and against the
+    order-2 jets of the same kernels combined with the same weights."""
+    g = load(name)
+    m = golden_model(name, g, eng)
+    x_np = g["pts0"]
+    n, d = x_np.shape
+    lap = LAPS[d]
+    x = torch.tensor(x_np).cuda()
+    e = m.jet_engine
+    out3, stash = e.forward(x, 3, need_stash=True, lap=lap)
+    assert out3.shape[0] == d + 2
+    prog, flat = AR.build_program(m)
+    ref3, cache = JR.forward(prog, flat, x_np.astype(np.float64), 3, lap)
+    assert relerr(out3.cpu().numpy().transpose(1, 0, 2), ref3) < TOL
+    out2, _ = e.forward(x, 2, need_stash=False)
+    comb = sum(lap[i] * out2[1 + d + i] for i in range(d))
+    assert relerr(out3[1 + d].cpu().numpy(), comb.cpu().numpy()) < TOL
+    assert relerr(out3[:1 + d].cpu().numpy(), out2[:1 + d].cpu().numpy()) < 1e-6
+    rng = np.random.default_rng(3)
+    dout_np = rng.standard_normal((n, d + 2, int(g["output_dim"]))).astype(np.float32)
+    dout = torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda()
+    dflat = e.backward(x, 3, dout, stash, lap=lap).cpu().numpy()
+    ref_dp, _ = JR.backward(prog, flat, x_np.astype(np.float64), 3, cache, dout_np.astype(np.float64), lap)
+    if prog[0, 0] == JR.OP_FOURIER:
+        ref_dp[prog[0, 3]: prog[0, 3] + prog[0, 1] * prog[0, 2] // 2] = 0
+    assert relerr(dflat, ref_dp) < TOL
+
+
+@pytest.mark.parametrize("name,dim", [("poisson_2D_1C", 2), ("navier_stokes_2D", 2), ("navier_stokes_3D", 3)])
+def test_laplace_mode_full_depth_many_tiles(name, dim):
+    """BASELINE depth, more tiles than CTAs, ragged tail, tcgen05 engine."""
+    m, _, _ = full_model(name, 5, _lib.ENGINE_TCGEN05)
+    n = 148 * 128 * 2 + 77
+    lap = (1.0,) * dim
+    rng = np.random.default_rng(9)
+    x_np = rng.random((n, dim), dtype=np.float32) * 0.5
+    x = torch.tensor(x_np).cuda()
+    out, stash = m.jet_engine.forward(x, 3, need_stash=True, lap=lap)
+    dout_np = rng.standard_normal((n, dim + 2, out.shape[2])).astype(np.float32)
+    dflat = m.jet_engine.backward(x, 3, torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda(),
+                                  stash, lap=lap).cpu().numpy()
+    prog, flat = AR.build_program(m)
+    ref, cache = JR.forward(prog, flat, x_np.astype(np.float64), 3, lap)
+    ref_dp, _ = JR.backward(prog, flat, x_np.astype(np.float64), 3, cache, dout_np.astype(np.float64), lap)
+    if prog[0, 0] == JR.OP_FOURIER:
+        ref_dp[prog[0, 3]: prog[0, 3] + prog[0, 1] * prog[0, 2] // 2] = 0
+    assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref) < TOL
+    assert relerr(dflat, ref_dp) < TOL
+
+
+def test_laplace_mode_property_at_1M_points():
+    """BASELINE configs[1] size: the L channel equals u_xx + u_yy of the order-2 launch at every one of 1M points,
+    and the reverse pass with seeds (g on L) equals the order-2 reverse pass with seeds (g on u_xx, g on u_yy)."""
+    m, _, _ = full_model("poisson_2D_1C", 11)
+    n = 1_000_000
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((n, 2), device="cuda", generator=gen) * 0.5
+    e = m.jet_engine
+    out3, st3 = e.forward(x, 3, need_stash=True, lap=(1.0, 1.0))
+    out2, st2 = e.forward(x, 2, need_stash=True)
+    lap2 = out2[3] + out2[4]
+    scale = float(lap2.abs().max())
+    assert float((out3[3] - lap2).abs().max()) / scale < TOL
+    assert torch.equal(out3[0], out2[0])
+    d3 = torch.randn(out3.shape, device="cuda", generator=gen)
+    d2 = torch.cat([d3[:3], d3[3:4], d3[3:4]], dim=0).contiguous()
+    g3 = e.backward(x, 3, d3, st3, lap=(1.0, 1.0))
+    g2 = e.backward(x, 2, d2, st2)
+    assert float((g3 - g2).abs().max() / g2.abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------------------ residual-program kernel
+@pytest.mark.parametrize("name", NAMES)
+def test_residual_kernel_matches_oracle_interpreter(name, cuda_backend):
+    """values, sums of squares and reverse-pass seeds of every traced example condition: device vs the numpy
+    interpreter in fp64 on the same jets; the values also equal the reference's residual vectors (goldens)."""
+    g = load(name)
+    model, conds, pinn = golden_pinn(name, g)
+    k = 0
+    for ci, c in enumerate(conds):
+        prog = c.program_for(model)
+        assert prog is not None, c.trace_note
+        x = torch.tensor(g[f"pts{ci}"]).cuda()
+        n = x.shape[0]
+        r = ConditionRunner(c, prog, model.jet_engine)
+        r.bind(n, x.device)
+        r.x.copy_(x)
+        K = len(prog.outputs)
+        w = torch.rand(K, device="cuda") + 0.5
+        sums = torch.zeros(K, device="cuda")
+        vals = torch.empty((K, n), device="cuda")
+        r._forward_blocks(r.x, r.blocks, True)
+        cuda_backend.residual_program(prog, r.x, [b.out for b in r.blocks], [b.dout for b in r.blocks], w, sums, vals)
+        jets = [b.out.cpu().numpy().astype(np.float64) for b in r.blocks]
+        rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
+                                 x.cpu().numpy().astype(np.float64), jets, w.cpu().numpy().astype(np.float64))
+        assert relerr(vals.cpu().numpy(), rv) < 2e-6
+        assert relerr(sums.cpu().numpy(), rs) < 2e-6
+        for b, ref in zip(r.blocks, rd):
+            assert relerr(b.dout.cpu().numpy(), ref) < 2e-6
+        for kk in range(K):
+            assert relerr(vals[kk].cpu().numpy(), g[f"res{ci}_{k}_f64"]) < TOL, (ci, k)
+            k += 1
+
+
+def test_residual_kernel_every_opcode(cuda_backend):
+    """A synthetic program touching every opcode, ragged sizes, against the numpy interpreter."""
+    model = mp.FNN(2, 2, [64, 64, 64]).cuda()
+
+    def fn(m, a):
+        u, v = mp.unpack(m(a))
+        x, y = mp.unpack(a)
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        t = torch.tanh(u) * torch.exp(-v) + torch.abs(u_x) / (2.0 + torch.cos(x) ** 2)
+        s = torch.sqrt(y * y + 1.0) - torch.log(x + 1.5) + torch.relu(u_y) - (-v) ** 3 + (u * u + 1.0) ** 0.75
+        return [t + torch.sin(s), s - 0.5 * t, u / (1.0 + v * v)]
+
+    prog = trace.trace_residual(fn, model, 2, torch.zeros(1, 2, device="cuda"))
+    ops = {i[0] for i in prog.instrs}
+    for need in (trace.OP_DIV, trace.OP_NEG, trace.OP_SIN, trace.OP_COS, trace.OP_EXP, trace.OP_TANH, trace.OP_RELU,
+                 trace.OP_ABS, trace.OP_SQRT, trace.OP_LOG, trace.OP_POWI, trace.OP_POWF):
+        assert need in ops
+    c = mp.Condition(fn, mp.Hypercube([0, 0], [1, 1]))
+    for n in (1, 127, 128, 129, 5000):
+        x = torch.rand((n, 2), device="cuda")
+        out, _ = model.jet_engine.forward(x, 1, need_stash=False)
+        dout = torch.empty_like(out)
+        K = 3
+        w = torch.tensor([0.3, 1.0, 2.5], device="cuda")
+        sums = torch.zeros(K, device="cuda")
+        vals = torch.empty((K, n), device="cuda")
+        cuda_backend.residual_program(prog, x, [out], [dout], w, sums, vals)
+        rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [2], x.cpu().numpy().astype(np.float64),
+                                 [out.cpu().numpy().astype(np.float64)], w.cpu().numpy().astype(np.float64))
+        assert relerr(vals.cpu().numpy(), rv) < 5e-6, n
+        assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
+        assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n
+        # value-only launch (no seeds), point-major layout
+        vt = torch.empty((n, K), device="cuda")
+        cuda_backend.residual_program(prog, x, [out], None, None, None, vt, point_major=True)
+        assert torch.equal(vt.t().contiguous(), vals)
+
+
+# ------------------------------------------------------------------------------ fused step
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_graph_step_matches_reference_golden(name):
+    """TrainerOneBatch on the fused path with CUDA graphs: losses, gradient and the 3-step Adam trajectory of the
+    unmodified reference; two more steps are graph replays and must keep agreeing with the eager jet path."""
+    g = load(name)
+    model, conds, pinn = golden_pinn(name, g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=5, update_grid_every=10**9)
+    fs = tr.fused_step()
+    assert fs is not None and tr._flat_adam is not None
+    # eager twin on identical weights
+    model_e, conds_e, pinn_e = golden_pinn(name, g)
+    opt_e = torch.optim.Adam(model_e.parameters(), lr=1e-3)
+    sched_e = torch.optim.lr_scheduler.ExponentialLR(opt_e, gamma=0.9999)
+    tr_e = mp.TrainerOneBatch(pinn_e, opt_e, sched_e, num_epochs=5, update_grid_every=10**9)
+    tr_e.use_fused_step = False
+    traj = []
+    for e in range(5):
+        tr.current_epoch = tr_e.current_epoch = e + 1
+        tr._train_epoch()
+        tr_e._train_epoch()
+        sched.step()
+        sched_e.step()
+        traj.append(float(tr.total_loss))
+        if e == 0:
+            assert relerr(tr.epoch_loss_detailed.cpu().numpy(), g["losses_f64"]) < TOL
+            assert relerr(model.jet_engine.flat_grad.cpu().numpy(), g["grad_f64"]) < TOL
+            assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - g["params_after1"]).max() < 5e-6
+        if e == 2:
+            assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - g["params_after3"]).max() < 1e-5
+        assert relerr(float(tr.total_loss), float(tr_e.total_loss)) < 2e-5, e
+        assert relerr(tr.epoch_loss_detailed.cpu().numpy(), tr_e.epoch_loss_detailed.cpu().numpy()) < 2e-5, e
+    assert relerr(np.array(traj[:3]), g["traj_f32"]) < 2e-5
+    assert fs.graph_replays >= 4            # steps 3..5: compute + update graphs
+    d = (model.jet_engine.flat.detach() - model_e.jet_engine.flat.detach()).abs().max()
+    assert float(d) < 2e-5
+    assert float(opt.state[next(model.parameters())]["step"]) == 5.0
+
+
+def test_fused_step_follows_new_points_and_lr(cuda_backend):
+    """A captured step must see points regenerated every epoch (update_grid_every=1, the reference default) and a
+    learning rate changed by the scheduler."""
+    torch.manual_seed(0)
+    model = mp.FNN(2, 1, [64, 64, 64]).cuda()
+    model_e = mp.FNN(2, 1, [64, 64, 64]).cuda()
+    model_e.load_state_dict(model.state_dict())
+
+    def inner(m, arg):
+        (u,) = mp.unpack(m(arg))
+        xx, yy = mp.unpack(arg)
+        u_x, u_y = mp.unpack(mp.grad(u, arg))
+        u_xx, _ = mp.unpack(mp.grad(u_x, arg))
+        _, u_yy = mp.unpack(mp.grad(u_y, arg))
+        return [u_xx + u_yy + torch.sin(xx) * yy]
+
+    trainers = []
+    for mdl, fused in ((model, True), (model_e, False)):
+        cond = mp.Condition(inner, mp.Hypercube([0, 0], [1, 1]))
+        pts = [torch.rand((700, 2), generator=torch.Generator().manual_seed(s)).cuda().requires_grad_() for s in range(6)]
+        cond.generator = types.SimpleNamespace(n_points=700, it=iter(pts),
+                                               generate=lambda c, m, it=iter(pts): next(it))
+        pinn = mp.PINN(mdl, [cond])
+        opt = torch.optim.Adam(mdl.parameters(), lr=1e-3)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5)
+        tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=6, update_grid_every=1)
+        tr.use_fused_step = fused
+        trainers.append((tr, sched))
+    for e in range(6):
+        for tr, sched in trainers:
+            tr.current_epoch = e
+            tr._train_epoch()
+            sched.step()
+        a, b = trainers[0][0], trainers[1][0]
+        assert relerr(float(a.total_loss), float(b.total_loss)) < 2e-5, e
+    assert trainers[0][0].fused_step().graph_replays >= 6
+    assert float((model.jet_engine.flat.detach() - model_e.jet_engine.flat.detach()).abs().max()) < 2e-5
+
+
+def test_adam_device_state_matches_torch_adam(cuda_backend):
+    torch.manual_seed(0)
+    n = 33_537
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_()
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    state = torch.zeros(4, device="cuda")
+    for step in range(1, 8):
+        gr = torch.randn(n, device="cuda") * 10.0 ** float(torch.randint(-6, 2, (1,)))
+        ref.grad = gr.clone()
+        state[0] = opt.param_groups[0]["lr"]
+        opt.step()
+        sched.step()
+        cuda_backend.adam_tick(state, 0.9, 0.999)
+        cuda_backend.adam_step_dev(p, gr, m, v, state, 0.9, 0.999, 1e-8, 1.0)
+        assert float(state[1]) == float(step)
+        assert float((p - ref.detach()).abs().max()) < 1e-6
+    assert float((m - opt.state[ref]["exp_avg"]).abs().max()) < 1e-6 * float(m.abs().max())
+
+
+# ------------------------------------------------------------------------------ C ABI corner cases
+def test_forward_without_stash_through_the_c_abi(cuda_backend):
+    """stash = NULL is a value-only pass: the FP32-FMA engine accepts it, ENGINE_AUTO falls to it, and an explicit
+    tcgen05 request is refused with a message (never an uninitialised return code)."""
+    m, _, _ = full_model("poisson_2D_1C", 2)
+    e = m.jet_engine
+    x = torch.rand((300, 2), device="cuda")
+    ref, _ = e.forward(x, 2, need_stash=True)
+    ops = m.jet_program()
+    for eng_id in (_lib.ENGINE_FFMA, _lib.ENGINE_AUTO):
+        out = torch.empty_like(ref)
+        cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 2, out, None, eng_id)
+        assert relerr(out.cpu().numpy(), ref.cpu().numpy()) < TOL
+    with pytest.raises(RuntimeError, match="stash"):
+        cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 2, torch.empty_like(ref), None, _lib.ENGINE_TCGEN05)
+    with pytest.raises(RuntimeError, match="lap_coef"):
+        cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 3, torch.empty((4, 300, 1), device="cuda"), None)
+    assert cuda_backend.engine_supports(ops, 2, 3, _lib.ENGINE_TCGEN05)
+    b, _, _ = full_model("burgers_1D", 2)
+    assert not cuda_backend.engine_supports(b.jet_program(), 2, 2, _lib.ENGINE_TCGEN05)
+    # a 128-wide program (FMA engine only) needs no stash for inference
+    with torch.no_grad():
+        y = b(torch.rand((64, 2), device="cuda"))
+    assert y.shape == (64, 1)
+
+
+def test_reloading_weights_invalidates_packed_operands():
+    """load_state_dict / in-place edits after a trainer took over the engine must reach the kernels."""
+    g = load("poisson_2D_1C")
+    model, conds, pinn = golden_pinn("poisson_2D_1C", g)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-2), None, num_epochs=2,
+                            update_grid_every=10**9)
+    x = torch.tensor(g["pts0"]).cuda()
+    with torch.no_grad():
+        y0 = model(x).clone()
+    tr.current_epoch = 1
+    tr._train_epoch()
+    with torch.no_grad():
+        y1 = model(x).clone()
+    assert not torch.equal(y0, y1)
+    model.load_state_dict(sd0)
+    with torch.no_grad():
+        assert torch.equal(model(x), y0)
+
+
+# ------------------------------------------------------------------------------ regularizers on CUDA
+@pytest.mark.parametrize("kind", ["normal", "pointwise"])
+def test_regularizers_match_reference_on_cuda(kind):
+    """NormalLosses / PointwiseLosses over 3 steps vs the reference's own run (tests/golden), on the device."""
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", f"poisson_{kind}_reg.npz"))
+    model, conds, pinn = golden_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.NormalLosses(alpha=0.9) if kind == "normal" else mp.PointwiseLosses(ignored_indexes=[1], lr=0.01)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    for e in range(3):
+        tr.current_epoch = e + 1
+        tr._train_epoch()
+        if kind == "normal":
+            assert relerr(reg.lambda_regularization.cpu().numpy(), gr["lambdas"][e]) < 5e-4
+        else:
+            ms = reg.models[0]
+            lam = np.concatenate([ms[0].weight.detach().cpu().numpy().reshape(-1)[:16],
+                                  ms[-1].weight.detach().cpu().numpy().reshape(-1)[:16]])
+            assert relerr(lam, gr["lambdas"][e]) < 2e-5
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 2e-5
+        assert relerr(tr.epoch_loss_detailed.cpu().numpy(), gr["losses"][e]) < 2e-5
+    assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - gr["params_after3"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D"])
+def test_points_grad_matches_reference_backward_on_cuda(name):
+    g = load(name)
+    model, conds, pinn = golden_pinn(name, g)
+    model.jet_engine.points_grad = True
+    pinn.select_batch(0)
+    total, _ = pinn.calculate_mean_loss()
+    total.backward()
+    fn, kind, _ = problems.CONFIGS[name]
+    spec, din, dout = fn(types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack, Symbols=None))
+    ref = AR.MODELS[kind](int(g["input_dim"]), int(g["output_dim"]), **GOLD_KW[name]).double()
+    ref.load_state_dict({k: torch.tensor(g["w::" + k]).double() for k in g["state_keys"]})
+    pts = [torch.tensor(g[f"pts{i}"]).double().requires_grad_() for i in range(len(spec))]
+    res = [r for (f, _), x in zip(spec, pts) for r in f(ref, x)]
+    (sum((r ** 2).sum() for r in res) / sum(r.numel() for r in res)).backward()
+    for c, x in zip(conds, pts):
+        assert c.points.grad is not None
+        assert relerr(c.points.grad.cpu().numpy(), x.grad.numpy()) < TOL

@@ -298,9 +298,8 @@ def test_full_depth_step_vs_fp64_autograd(name):
     assert relerr(total.item(), rtotal.item()) < TOL
     assert relerr(torch.stack(losses).detach().cpu().numpy(), rlosses.detach().cpu().numpy()) < TOL
     # The parameter gradient is a sum over thousands of points; its fp32 round-off floor is set by the
-    # summation, not by the jets.  Measure that floor with the reference algorithm itself (same nested
-    # autograd, fp32, same device) and require ours to be within 1e-5 or 4x that floor of fp64 truth
-    # (measured round 1, FFMA engine: ours 1.5e-5 vs reference-fp32 5.1e-6 on poisson; equal elsewhere).
+    # summation, not by the jets.  The reference algorithm's own fp32 floor (same nested autograd, fp32, same
+    # device) is measured and printed beside ours; the gate is the plain 1e-5 of BASELINE.md.
     ref32 = AR.MODELS[kind](din, dout, **problems.CONFIGS[name][2]).cuda()
     ref32.load_state_dict(model.state_dict())
     t32, _ = AR.mean_loss(ref32, [fn for fn, _ in spec_r],
@@ -311,7 +310,7 @@ def test_full_depth_step_vs_fp64_autograd(name):
     floor = relerr(g32, rgrad)
     ours = relerr(model.jet_engine.flat_grad.cpu().numpy(), rgrad)
     print(f"{name}: param-grad rel err ours {ours:.2e}, reference fp32 autograd {floor:.2e}")
-    assert ours < max(TOL, 4.0 * floor)
+    assert ours < TOL      # BASELINE.md's W.grad gate, not relaxed by the reference's own fp32 floor
 
 
 # ------------------------------------------------------------------------------ size-independent properties

@@ -1,0 +1,295 @@
+"""Residual tracing (multipinn_b200/trace.py), the Laplace-mode rewrite and the fused train step
+(multipinn_b200/fused.py), exercised on CPU with the oracle standing in for the kernels and checked against the
+vectors of the unmodified reference (tests/golden)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import multipinn_b200 as mp
+from multipinn_b200 import engine, jet, trace
+from multipinn_b200.fused import ConditionRunner
+from oracle import jet_ref as JR
+from oracle import residual_ref as RR
+from tests import problems
+from tests.oracle_backend import OracleBackend
+from tests.test_host_cpu import build_pinn, product_model, product_ns
+from tests.test_oracle_golden import NAMES, load, relerr
+
+
+@pytest.fixture(autouse=True)
+def oracle_backend():
+    be = OracleBackend()
+    old = engine._set_backend_for_tests(be)
+    jet.clear_blocks()
+    yield be
+    engine._set_backend_for_tests(old)
+
+
+# what the tracer must find for the five BASELINE configs: (order, Laplace weights) of the domain condition
+EXPECT_DOMAIN = {
+    "regression_1D": (0, None),
+    "poisson_2D_1C": (3, (1.0, 1.0)),
+    "burgers_1D": (3, (1.0, 0.0)),
+    "allen_cahn_2D_1C": (3, (1.0, 0.0)),
+    "navier_stokes_2D": (3, (1.0, 1.0)),
+    "navier_stokes_3D": (3, (1.0, 1.0, 1.0)),
+}
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_every_example_condition_is_traced(name):
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    for c in conds:
+        assert c.program_for(model) is not None, c.trace_note
+    blk = conds[0].program_for(model).blocks[0]
+    order, lap = EXPECT_DOMAIN[name]
+    assert blk.order == order
+    assert (blk.lap if order == 3 else None) == lap
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_traced_residuals_match_reference_golden(name):
+    """values of the device program == the residual vectors of the unmodified reference (fp64 goldens)."""
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    k = 0
+    for ci, c in enumerate(conds):
+        prog = c.program_for(model)
+        vals = ConditionRunner(c, prog, model.jet_engine).residual_values(torch.tensor(g[f"pts{ci}"]))
+        for kk in range(vals.shape[0]):
+            assert relerr(vals[kk].numpy(), g[f"res{ci}_{k}_f64"]) < 1e-5, (ci, k)
+            k += 1
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", ["mean", "legacy"])
+def test_fused_step_loss_and_gradient_match_reference(name, mode, oracle_backend):
+    """One fused step (no autograd): losses and the flat parameter gradient equal the reference's
+    ``calculate_mean_loss`` / ``backward`` (goldens); the eager path gives the same numbers."""
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)   # not Adam: the step leaves the gradient untouched
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=1, update_grid_every=10**9, calc_loss=mode)
+    assert tr.fused_step() is not None
+    oracle_backend.calls.clear()
+    pinn.select_batch(0)
+    tr._train_batches()
+    kinds = [c[0] for c in oracle_backend.calls]
+    assert "resid" in kinds and "bwd" in kinds
+    assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_f64"]) < 1e-5
+    want_total = g["total_f64"] if mode == "mean" else g["legacy_f64"]
+    assert relerr(tr.total_loss.numpy(), want_total) < 1e-5
+    if mode == "mean":
+        assert relerr(model.jet_engine.flat_grad.numpy(), g["grad_f64"]) < 1e-5
+    # and the eager jet path agrees with the fused one
+    fused_grad = model.jet_engine.flat_grad.clone()
+    tr.use_fused_step = False
+    tr.total_loss, tr.epoch_loss_detailed = 0, None
+    tr._train_batches()
+    assert relerr(model.jet_engine.flat_grad.numpy(), fused_grad.numpy()) < 1e-6
+    assert relerr(tr.total_loss.numpy(), want_total) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D", "regression_1D"])
+def test_fused_adam_trajectory_matches_reference(name):
+    """3 TrainerOneBatch steps with Adam through the fused path (device-side lr / step state) land on the
+    reference's weights (goldens params_after1 / params_after3)."""
+    g = load(name)
+    model, conds, pinn = build_pinn(name, g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.999)
+    tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=2, update_grid_every=10**9)
+    assert tr.fused_step() is not None and tr._flat_adam is not None
+    flat = model.jet_engine.flat
+    for step in range(3):
+        tr.current_epoch = step
+        tr._train_epoch()
+        sched.step()
+        if step == 0:
+            assert relerr(flat.detach().numpy(), g["params_after1"]) < 2e-5
+            assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_step1"]) < 1e-5
+    assert relerr(flat.detach().numpy(), g["params_after3"]) < 5e-5
+    assert float(opt.state[next(model.parameters())]["step"]) == 3.0
+
+
+def _trace(fn, model, d=2):
+    return trace.trace_residual(fn, model, d, torch.zeros(1, d))
+
+
+def _small_model(d=2, o=1):
+    torch.manual_seed(0)
+    return mp.FNN(d, o, [16, 16])
+
+
+def test_laplace_rewrite_cases():
+    model = _small_model()
+
+    def sym(model, arg):
+        (u,) = mp.unpack(model(arg))
+        x, y = mp.unpack(arg)
+        u_x, u_y = mp.unpack(mp.grad(u, arg))
+        u_xx, _ = mp.unpack(mp.grad(u_x, arg))
+        _, u_yy = mp.unpack(mp.grad(u_y, arg))
+        return u, x, y, u_x, u_y, u_xx, u_yy
+
+    # anisotropic constant coefficients: one channel with weights (1, 0.25) up to scale
+    p = _trace(lambda m, a: [(lambda s: 4.0 * s[5] + s[6] - s[0])(sym(m, a))], model)
+    assert p.blocks[0].order == 3 and np.allclose(p.blocks[0].lap, (1.0, 0.25))
+    # two components with proportional combinations share the channel
+    p = _trace(lambda m, a: (lambda s: [s[5] + s[6], -3.0 * (s[5] + s[6]) / 2.0 + s[3]])(sym(m, a)), model)
+    assert p.blocks[0].order == 3 and p.blocks[0].lap == (1.0, 1.0)
+    # non-proportional combinations, non-constant coefficients and non-linear uses keep the full order-2 block
+    p = _trace(lambda m, a: (lambda s: [s[5] + s[6], s[5] - s[6]])(sym(m, a)), model)
+    assert p.blocks[0].order == 2
+    p = _trace(lambda m, a: (lambda s: [s[1] * s[5] + s[6]])(sym(m, a)), model)
+    assert p.blocks[0].order == 2
+    p = _trace(lambda m, a: (lambda s: [s[5] * s[5] + s[6]])(sym(m, a)), model)
+    assert p.blocks[0].order == 2
+    p = _trace(lambda m, a: (lambda s: [torch.sin(s[5] + s[6])])(sym(m, a)), model)
+    assert p.blocks[0].order == 2
+    # derivatives that are requested but never used do not raise the block's order
+    p = _trace(lambda m, a: (lambda s: [s[0] - s[1]])(sym(m, a)), model)
+    assert p.blocks[0].order == 0
+    p = _trace(lambda m, a: (lambda s: [s[3] * s[0]])(sym(m, a)), model)
+    assert p.blocks[0].order == 1
+
+
+def _eval(prog, model, x, lap_check=True):
+    """Program values on the fp64 oracle jets."""
+    ops, flat = model.jet_program(), model.jet_engine
+    flat.ensure_flat()
+    params = flat.flat.detach().numpy().astype(np.float64)
+    jets = []
+    for b, blk in enumerate(prog.blocks):
+        xb = x
+        pp = prog.points_program(b)
+        if pp is not None:
+            vals, _, _ = RR.evaluate(pp.instrs, pp.consts, pp.outputs, [], x, [], want_seeds=False)
+            xb = np.ascontiguousarray(vals.T)
+        o, _ = JR.forward(ops, params, xb, blk.order, blk.lap)
+        jets.append(o.transpose(1, 0, 2))
+    return RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks], x, jets)
+
+
+def test_laplace_mode_equals_full_second_order():
+    """The rewritten program on Laplace-mode jets == the eager residual on full order-2 jets, values and seeds
+    mapped back (d L / d u_ii = c_i d L / d L-channel)."""
+    model = _small_model()
+    rng = np.random.default_rng(1)
+    x = rng.random((33, 2))
+
+    def fn(m, a):
+        (u,) = mp.unpack(m(a))
+        xx, yy = mp.unpack(a)
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        u_xx, _ = mp.unpack(mp.grad(u_x, a))
+        _, u_yy = mp.unpack(mp.grad(u_y, a))
+        return [0.5 * u_xx + 2.0 * u_yy + u * u_x - torch.exp(xx) * yy, u_y**2 - (u_xx * 0.25 + u_yy)]
+
+    prog = _trace(fn, model)
+    assert prog.blocks[0].order == 3 and np.allclose(prog.blocks[0].lap, (0.25, 1.0))
+    vals, sums, dj = _eval(prog, model, x)
+    with mp.jet_order(2):
+        xt = torch.tensor(x, dtype=torch.float32).requires_grad_()
+        eager = fn(model, xt)
+    for k in range(2):
+        assert relerr(vals[k], eager[k].detach().numpy().astype(np.float64)) < 1e-6
+
+
+def test_multi_block_programs_shifted_points():
+    g = load("regression_1D")
+    model, conds, pinn = build_pinn("regression_1D", g)
+    prog = conds[0].program_for(model)
+    assert len(prog.blocks) == 2 and prog.blocks[0].points is None and prog.blocks[1].points is not None
+    pp = prog.points_program(1)
+    x = np.linspace(0, 1, 5).reshape(-1, 1)
+    vals, _, _ = RR.evaluate(pp.instrs, pp.consts, pp.outputs, [], x, [], want_seeds=False)
+    assert np.allclose(vals[0], x[:, 0] + 1.0)
+    g = load("burgers_1D")
+    model, conds, pinn = build_pinn("burgers_1D", g)
+    prog = conds[1].program_for(model)     # periodic boundary: model(arg) and model(arg shifted by 2 in x)
+    assert len(prog.blocks) == 2
+    pp = prog.points_program(1)
+    x = np.array([[-1.0, 0.3], [-1.0, 0.7]])
+    vals, _, _ = RR.evaluate(pp.instrs, pp.consts, pp.outputs, [], x, [], want_seeds=False)
+    assert np.allclose(vals.T, x + np.array([2.0, 0.0]))
+
+
+def test_untraceable_residuals_fall_back_to_eager(oracle_backend):
+    model = _small_model()
+    geo = mp.Hypercube([0, 0], [1, 1])
+
+    def branching(m, a):
+        (u,) = mp.unpack(m(a))
+        return [u if bool((u > 0).all()) else -u]          # data-dependent control flow
+
+    def batch_reduction(m, a):
+        (u,) = mp.unpack(m(a))
+        return [u - u.mean()]                               # couples the points of a batch
+
+    def derived_grad(m, a):
+        (u,) = mp.unpack(m(a))
+        return [u * 2.0]
+
+    for fn in (branching, batch_reduction):
+        c = mp.Condition(fn, geo)
+        c.init_output_len(model)
+        assert c.program_for(model) is None and c.trace_note
+        assert c.output_len == 1
+    c = mp.Condition(derived_grad, geo)
+    c.init_output_len(model)
+    assert c.program_for(model) is not None
+    # a trainer with an untraced condition stays on the eager path and still trains
+    c1, c2 = mp.Condition(batch_reduction, geo), mp.Condition(derived_grad, geo)
+    for c in (c1, c2):
+        mp.Generator(16, "pseudo").use_for(c)
+    pinn = mp.PINN(model, [c1, c2])
+    tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-3), None, num_epochs=1)
+    assert tr.fused_step() is None
+    tr._train_epoch()
+    assert np.isfinite(float(tr.total_loss))
+
+
+def test_mixed_derivative_is_rejected_when_used_and_harmless_when_not():
+    model = _small_model()
+
+    def unused(m, a):
+        (u,) = mp.unpack(m(a))
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        u_xx, u_xy = mp.unpack(mp.grad(u_x, a))
+        return [u_xx - u]
+
+    def used(m, a):
+        (u,) = mp.unpack(m(a))
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        u_xx, u_xy = mp.unpack(mp.grad(u_x, a))
+        return [u_xy + u]
+
+    assert _trace(unused, model).blocks[0].order == 3
+    with pytest.raises(mp.UnsupportedDerivative):
+        _trace(used, model)
+
+
+def test_program_struct_roundtrip_and_limits():
+    g = load("navier_stokes_3D")
+    model, conds, pinn = build_pinn("navier_stokes_3D", g)
+    prog = conds[0].program_for(model)
+    st = prog.struct()
+    assert st.n_instr == len(prog.instrs) and st.n_out == 4 and st.n_blocks == 1
+    assert st.block_J[0] == 5 and st.block_o[0] == 4     # Laplace mode: value, 3 first derivatives, L
+    loads = [(i, ins) for i, ins in enumerate(prog.instrs) if ins[0] == trace.OP_LOADJ]
+    for i, (_, a, b, _) in loads:
+        assert st.jet_reg[a][b] == i
+    model2 = _small_model()
+
+    def long(m, a):
+        (u,) = mp.unpack(m(a))
+        for _ in range(200):
+            u = u * 1.5 + 0.25
+        return [u]
+
+    with pytest.raises(trace.TraceError):
+        _trace(long, model2)

@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpinn_b200.so")
+# MPINN_B200_LIB selects a diagnostic build of the same library (scripts/build_variant.sh); it is never a fallback
+LIB_PATH = os.environ.get("MPINN_B200_LIB") or os.path.join(_HERE, "csrc", "libmpinn_b200.so")
 
 ABI_VERSION = 2
 OP_LINEAR, OP_FOURIER = 0, 1

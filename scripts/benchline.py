@@ -2,7 +2,8 @@
 import json
 import sys
 
-for line in sys.stdin:
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for line in src:
     if not line.startswith("{"):
         print(line.rstrip()[:200])
         continue

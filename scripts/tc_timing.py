@@ -9,12 +9,14 @@ m = mp.FNN(2, 1, [64] * 9).cuda()
 e = m.jet_engine
 n = 148 * 128 * 8
 x = torch.rand(n, 2, device="cuda") * 0.5
-out, stash = e.forward(x, 2, True)
+ORDER = int(os.environ.get("TC_ORDER", "3"))
+LAP = (1.0, 1.0) if ORDER == 3 else None
+out, stash = e.forward(x, ORDER, True, lap=LAP)
 dout = torch.randn_like(out)
 lib = _lib.load()
 buf = (ctypes.c_longlong * 32)()
 lib.mpinn_debug_counters(buf, 32)
-e.backward(x, 2, dout, stash)
+e.backward(x, ORDER, dout, stash, lap=LAP)
 lib.mpinn_debug_counters(buf, 32)
 names = {15: "tile start", 0: "output op", 1: "layer setup (coeffs, cache fill, W)", 2: "phase: loads + zbar chunk0", 3: "phase: wait prev GEMMs",
          4: "phase: rest of staging", 5: "phase: barrier", 6: "phase: MMA issue", 7: "layer: final GEMM wait", 8: "layer: dW flush", 9: "op0 + tail"}
@@ -27,7 +29,7 @@ for th, label in ((0, "thread 0 (issuer)"), (1, "thread 224")):
 
 # ---- forward
 lib.mpinn_debug_counters(buf, 32)
-out, stash = e.forward(x, 2, True)
+out, stash = e.forward(x, ORDER, True, lap=LAP)
 lib.mpinn_debug_counters(buf, 32)
 names = {15: "tile start", 10: "layer: W tile load", 11: "channel: source + activation math chunk0", 12: "channel: wait A buffer",
          13: "channel: rest of staging", 14: "channel: barrier", 6: "channel: MMA issue", 7: "layer: end GEMM wait", 9: "output op"}

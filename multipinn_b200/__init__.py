@@ -12,10 +12,13 @@ from .geometry import Hypercube
 from .jet import jet_order
 from .neural_network import FFNN, FNN, FourierFeatureNetwork, ResNet, XavierFNN
 from .PINN import PINN
-from .regularization import ConstantLosses, GradientLosses, NormalLosses, PointwiseLosses
+from .install import install, uninstall
+from .regularization import (AdaptiveConditionsAndPointsLosses, AdaptiveConditionsLosses, ConstantLosses,
+                             GradientLosses, NormalLosses, PointwiseLosses)
 from .trainer import Trainer, TrainerMultiGPU, TrainerOneBatch
 
 __version__ = "0.1.0"
 __all__ = ["neural_network", "Condition", "ConditionExtra", "Symbols", "grad", "unpack", "Generator",
            "Hypercube", "jet_order", "FNN", "XavierFNN", "ResNet", "FourierFeatureNetwork", "FFNN",
-           "PINN", "ConstantLosses", "GradientLosses", "NormalLosses", "PointwiseLosses", "Trainer", "TrainerOneBatch", "TrainerMultiGPU", "UnsupportedDerivative"]
+           "PINN", "ConstantLosses", "GradientLosses", "NormalLosses", "PointwiseLosses", "AdaptiveConditionsLosses",
+           "AdaptiveConditionsAndPointsLosses", "install", "uninstall", "Trainer", "TrainerOneBatch", "TrainerMultiGPU", "UnsupportedDerivative"]

@@ -271,6 +271,8 @@ class JetEngine:
         for p, off in zip(self._params, self._offsets):
             if p.requires_grad:
                 p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+            else:
+                p.grad = None   # frozen after the buffers were built: optimizers must not see a gradient
 
     def zero_grad(self):
         self.ensure_flat()

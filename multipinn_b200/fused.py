@@ -162,6 +162,7 @@ class FusedStep:
             if self.flat_adam is not None:
                 self.adam_state = torch.zeros(4, dtype=torch.float32, device=device)
                 self.adam_state[1] = float(self.flat_adam.step)
+                self._step_on_device = self.flat_adam.step
                 self._lr_on_device = None
 
     def _loss_view(self):
@@ -238,6 +239,8 @@ class FusedStep:
         fa = self.flat_adam
         if fa is None:
             return False
+        if fa.step != self._step_on_device:   # optimizer state was loaded from outside (checkpoint resume)
+            self.adam_state[1:2].fill_(float(fa.step))
         lr = float(fa.optimizer.param_groups[0]["lr"])
         if lr != self._lr_on_device:
             self.adam_state[0:1].fill_(lr)
@@ -247,6 +250,7 @@ class FusedStep:
             self._g_update = None
         self._graphed("_g_update", lambda: self._update(self._scale))
         fa.step += 1
+        self._step_on_device = fa.step
         fa.mark_stepped()
         self.engine.generation += 1      # parameters changed; operands were re-packed inside _update
         self.engine.packed_valid = True

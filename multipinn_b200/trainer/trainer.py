@@ -84,6 +84,13 @@ class _FlatAdam:
                             g["lr"], b1, b2, g["eps"], grad_scale)
         self.mark_stepped()
 
+    def load_state(self, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int):
+        """Resume from flat Adam moments (what a checkpoint of ``optimizer.state_dict()`` flattens to)."""
+        self.m.copy_(exp_avg.reshape(-1))
+        self.v.copy_(exp_avg_sq.reshape(-1))
+        self.step = int(step)
+        self._step_t.fill_(float(self.step))
+
     def mark_stepped(self):
         self._step_t.fill_(float(self.step))
         self.optimizer._opt_called = True  # what LRScheduler checks before its first step()
@@ -140,6 +147,7 @@ class Trainer:
         self._fused = None
         if self._engine is not None:
             self._engine.ensure_flat()
+            self._engine.attach_grads()
             self._engine.managed = True
             self._engine.invalidate()
             if _FlatAdam.eligible(self._engine, optimizer):

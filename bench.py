@@ -386,8 +386,15 @@ def run_ours(args):
     trainer.use_cuda_graphs = not args.no_graphs
 
     t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    replicas_in_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # data-parallel correctness on NCCL: after the same number of steps every rank must hold the same weights
+        flat = model.jet_engine.flat.detach().double()
+        mine = torch.stack([flat.sum(), flat.abs().sum(), (flat * flat).sum()])
+        allsums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+        replicas_in_sync = all(bool(torch.equal(a, allsums[0])) for a in allsums)
     ms, e2e_ms = float(t[0]), float(t[1])
 
     if rank == 0:
@@ -475,6 +482,8 @@ def run_ours(args):
             "roofline": roofline,
             "final_loss": final_loss,
         }
+        if replicas_in_sync is not None:
+            line["replicas_in_sync"] = replicas_in_sync
         if world == 1 and not args.no_baselines:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

@@ -157,14 +157,17 @@ typedef struct mpinn_rprog {
  *   values[k][n] = r_k[n]                                       (optional: what Condition.get_residual returns;
  *                                                                 values_point_major != 0 stores values[n][k] instead)
  * prog_host and the two pointer tables are HOST memory; jets[a] / djets[a] are device [J_a, n, o_a] blocks.
- * djets, weights (device [n_out]), sums (device [n_out]) and values may each be NULL.  A program without model
+ * djets, weights (device [n_out]), sums (device [n_out]) and values may each be NULL.  jet_stride (0 = n) is the
+ * number of points of the jet blocks when they are longer than this launch's n: several conditions of the same
+ * jet order share one forward / reverse launch over their concatenated points, and each condition's program runs on
+ * its slice (jets[a] / djets[a] then point at the slice's first point).  A program without model
  * calls (n_blocks == 0, jets_host NULL) is allowed: it maps point columns to point columns, which is how the points
  * of a second model call such as model(arg + 1) (reference examples/regression_1D/problem.py:17-35) or a shifted
  * boundary (examples/burgers_1D/problem.py:20-25) are produced on the device. */
 int mpinn_residual_program(const mpinn_rprog_t* prog_host, const float* x, int64_t n,
                            const float* const* jets_host, float* const* djets_host,
                            const float* weights, float* sums, float* values, int values_point_major,
-                           void* stream);
+                           int64_t jet_stride, void* stream);
 
 /* Adam with its scalar state on the device, so that a captured CUDA graph of the train step can be replayed
  * while the learning rate and the step count change: state = {lr, step, step_size, sqrt(1 - beta2^step)}.

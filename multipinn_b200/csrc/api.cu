@@ -33,7 +33,7 @@ cudaError_t read_tc_debug(long long* out, int n);
 // residual.cu
 cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
-                            int values_point_major, int sm_count, cudaStream_t stream);
+                            int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream);
 cudaError_t launch_adam_tick(float* state, float beta1, float beta2, cudaStream_t stream);
 cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* state,
                             float beta1, float beta2, float eps, float grad_scale, cudaStream_t stream);
@@ -343,10 +343,11 @@ int mpinn_engine_supports(const mpinn_op_t* ops, int n_ops, int d, int order, in
 
 int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n, const float* const* jets,
                            float* const* djets, const float* weights, float* sums, float* values,
-                           int values_point_major, void* stream) {
+                           int values_point_major, int64_t jet_stride, void* stream) {
   if (!prog || !x) return fail("null pointer");
   if (prog->n_blocks > 0 && !jets) return fail("residual program: null jet table");
   if (prog->n_blocks == 0 && djets) return fail("residual program: seeds requested without model calls");
+  if (jet_stride != 0 && jet_stride < n) return fail("residual program: jet_stride smaller than n");
   if (n <= 0) return 0;
   if (prog->n_instr < 1 || prog->n_instr > MPINN_RP_MAX_INSTR) return fail("residual program: bad instruction count");
   if (prog->n_out < 1 || prog->n_out > MPINN_RP_MAX_OUT) return fail("residual program: bad output count");
@@ -382,8 +383,8 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n,
   DeviceInfo info;
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
-  e = launch_residual(*prog, x, n, jets, djets, weights, sums, values, values_point_major, info.sm_count,
-                      (cudaStream_t)stream);
+  e = launch_residual(*prog, x, n, jets, djets, weights, sums, values, values_point_major, jet_stride,
+                      info.sm_count, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("residual_program", e);
   return 0;
 }

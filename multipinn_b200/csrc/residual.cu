@@ -39,7 +39,7 @@ template <bool SEEDS>
 __global__ void __launch_bounds__(kResidThreads)
 residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, const float* __restrict__ x,
                 int64_t n, const float* __restrict__ weights, float* __restrict__ sums,
-                float* __restrict__ values, int values_point_major) {
+                float* __restrict__ values, int values_point_major, int64_t jstride) {
   extern __shared__ float rp_smem[];
   const int t = threadIdx.x;
   const int NI = prog.n_instr;
@@ -63,7 +63,7 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
         case MPINN_RP_LOADJ: {
           const int o = prog.block_o[in.a];
           const int j = in.b / o, k = in.b - j * o;
-          r = __ldg(io.jets[in.a] + ((int64_t)j * n + pt) * o + k);
+          r = __ldg(io.jets[in.a] + ((int64_t)j * jstride + pt) * o + k);
         } break;
         case MPINN_RP_ADD: r = v[in.a * kResidThreads] + v[in.b * kResidThreads]; break;
         case MPINN_RP_SUB: r = v[in.a * kResidThreads] - v[in.b * kResidThreads]; break;
@@ -137,7 +137,7 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
       for (int jo = 0; jo < JO; ++jo) {
         const int reg = prog.jet_reg[b][jo];
         const int j = jo / o, k = jo - j * o;
-        dj[((int64_t)j * n + pt) * o + k] = reg >= 0 ? adj[reg * kResidThreads] : 0.0f;
+        dj[((int64_t)j * jstride + pt) * o + k] = reg >= 0 ? adj[reg * kResidThreads] : 0.0f;
       }
     }
   }
@@ -166,7 +166,8 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
 
 cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
-                            int values_point_major, int sm_count, cudaStream_t stream) {
+                            int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream) {
+  const int64_t jstride = jet_stride > 0 ? jet_stride : n;
   ResidIO io;
   for (int b = 0; b < MPINN_RP_MAX_BLOCKS; ++b) {
     io.jets[b] = (b < prog.n_blocks && jets) ? jets[b] : nullptr;
@@ -182,12 +183,12 @@ cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n
     e = cudaFuncSetAttribute(residual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     residual_kernel<true><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, n, weights, sums, values,
-                                                                             values_point_major);
+                                                                             values_point_major, jstride);
   } else {
     e = cudaFuncSetAttribute(residual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     residual_kernel<false><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, n, weights, sums, values,
-                                                                              values_point_major);
+                                                                              values_point_major, jstride);
   }
   return cudaGetLastError();
 }

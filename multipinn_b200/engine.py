@@ -114,22 +114,25 @@ class CudaBackend:
         CudaBackend.gpu_launches += 2
 
     def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
-                         point_major=False):
+                         point_major=False, jet_offset=0, jet_stride=0):
         """One launch: residual components of a traced program at the points ``x``; ``sums[k] += sum r_k^2``,
         ``djets[b]`` = seeds of the reverse pass for ``sum_k weights[k] sum_n r_k^2``, ``values[k, n] = r_k``
-        (``values[n, k]`` with ``point_major``)."""
+        (``values[n, k]`` with ``point_major``).  ``jet_offset`` / ``jet_stride``: the jet blocks hold ``jet_stride``
+        points and this launch works on the slice starting at point ``jet_offset`` (conditions batched into one
+        forward / reverse launch)."""
         st = prog.struct()
         nb = len(jets)
-        jp = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in jets]) if nb else None
+        offs = [jet_offset * b.o * 4 for b in prog.blocks]
+        jp = (ctypes.c_void_p * nb)(*[t.data_ptr() + o for t, o in zip(jets, offs)]) if nb else None
         dp = None
         if djets is not None:
-            dp = (ctypes.c_void_p * nb)(*[(t.data_ptr() if t is not None else 0) for t in djets])
+            dp = (ctypes.c_void_p * nb)(*[(t.data_ptr() + o if t is not None else 0) for t, o in zip(djets, offs)])
         for t in list(jets) + [t for t in (djets or []) if t is not None]:
             assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
         tok = self._timed("resid", x.shape[0], 0)
         _lib.check(self.lib.mpinn_residual_program(ctypes.byref(st), self._ptr(x), x.shape[0], jp, dp,
                                                    self._ptr(weights), self._ptr(sums), self._ptr(values),
-                                                   1 if point_major else 0, self._stream()),
+                                                   1 if point_major else 0, int(jet_stride), self._stream()),
                    "mpinn_residual_program")
         self._timed_end(tok)
         CudaBackend.gpu_launches += 1

@@ -44,6 +44,25 @@ class ConditionRunner:
             bb.x = bb.out = bb.dout = bb.stash = None
             self.blocks.append(bb)
 
+    # -- batching: conditions whose single model call has the same jet order share ONE forward and ONE reverse
+    #    launch over their concatenated points (fewer tail waves and launches); each keeps its own residual program,
+    #    which runs on its slice of the shared jet block
+    def batch_key(self):
+        if len(self.blocks) != 1 or self.blocks[0].points_prog is not None:
+            return None
+        bb = self.blocks[0]
+        return (bb.order, tuple(bb.lap) if bb.lap is not None else None)
+
+    def attach_shared(self, group, n0: int):
+        self.group, self.n0 = group, n0
+        self.n = group.counts[group.members.index(self)]
+        self.x = group.x[n0:n0 + self.n]
+
+    def launch_residual_shared(self, weights, sums):
+        g = self.group
+        backend().residual_program(self.prog, self.x, [g.out], [g.dout], weights, sums,
+                                   jet_offset=self.n0, jet_stride=g.n_total)
+
     def bind(self, n: int, device) -> bool:
         """(Re)allocate the static buffers for n points; True if they changed (a captured graph is then stale)."""
         if n == self.n and self.x is not None and self.x.device == device:
@@ -92,6 +111,43 @@ class ConditionRunner:
         return vals
 
 
+class BatchedGroup:
+    """Conditions with the same jet order evaluated by one forward and one reverse launch."""
+
+    def __init__(self, members: List[ConditionRunner]):
+        self.members = members
+        self.engine = members[0].engine
+        self.order = members[0].blocks[0].order
+        self.lap = members[0].blocks[0].lap
+        self.counts: List[int] = []
+        self.n_total = -1
+        self.x = self.out = self.dout = self.stash = None
+
+    def bind(self, device) -> bool:
+        counts = [int(m.cond.batch_points.shape[0]) for m in self.members]
+        if counts == self.counts and self.x is not None and self.x.device == device:
+            return False
+        eng = self.engine
+        self.counts, self.n_total = counts, sum(counts)
+        n = self.n_total
+        self.x = torch.empty((n, eng.d), dtype=torch.float32, device=device)
+        self.out = torch.empty((eng.n_jets(self.order), n, eng.n_out), dtype=torch.float32, device=device)
+        self.dout = torch.empty_like(self.out)
+        self.stash = torch.empty(eng.stash_floats(self.order, n), dtype=torch.float32, device=device)
+        n0 = 0
+        for m, c in zip(self.members, counts):
+            m.attach_shared(self, n0)
+            n0 += c
+        return True
+
+    def launch(self, weights, sums, dflat, k0s):
+        eng = self.engine
+        eng.forward(self.x, self.order, True, lap=self.lap, out=self.out, stash=self.stash)
+        for m, k0 in zip(self.members, k0s):
+            m.launch_residual_shared(weights[k0:k0 + m.K], sums[k0:k0 + m.K])
+        eng.backward_into(self.x, self.order, self.dout, self.stash, dflat, lap=self.lap)
+
+
 class FusedStep:
     """Whole-step executor for a trainer whose conditions are all traced."""
 
@@ -101,6 +157,25 @@ class FusedStep:
         self.flat_adam = flat_adam
         self.runners: List[ConditionRunner] = [ConditionRunner(c, p, engine) for c, p in zip(conditions, programs)]
         self.K = sum(r.K for r in self.runners)
+        self.k0 = []
+        k = 0
+        for r in self.runners:
+            self.k0.append(k)
+            k += r.K
+        # launch units, in condition order of their first member: single conditions or batched groups
+        self.batch_conditions = True
+        by_key, self.units = {}, []
+        for r in self.runners:
+            key = r.batch_key()
+            if key is None:
+                self.units.append(r)
+            elif key in by_key:
+                by_key[key].append(r)
+            else:
+                by_key[key] = [r]
+                self.units.append(by_key[key])
+        self.units = [(u if isinstance(u, ConditionRunner) else (BatchedGroup(u) if len(u) > 1 else u[0]))
+                      for u in self.units]
         self.use_graphs = use_graphs
         self._g_compute: Optional[torch.cuda.CUDAGraph] = None
         self._g_update: Optional[torch.cuda.CUDAGraph] = None
@@ -140,8 +215,11 @@ class FusedStep:
         eng = self.engine
         eng.ensure_flat()
         changed = device != self._dev
-        for r in self.runners:
-            changed |= r.bind(int(r.cond.batch_points.shape[0]), device)
+        for u in self.units:
+            if isinstance(u, BatchedGroup):
+                changed |= u.bind(device)
+            else:
+                changed |= u.bind(int(u.cond.batch_points.shape[0]), device)
         if changed:
             self._dev = device
             self._g_compute = self._g_update = None
@@ -175,10 +253,12 @@ class FusedStep:
         eng = self.engine
         eng.flat_grad.zero_()
         self.sums.zero_()
-        k0 = 0
-        for r in self.runners:
-            r.launch(self.weights[k0:k0 + r.K], self.sums[k0:k0 + r.K], eng.flat_grad)
-            k0 += r.K
+        for u in self.units:
+            if isinstance(u, BatchedGroup):
+                u.launch(self.weights, self.sums, eng.flat_grad, [self.k0[self.runners.index(m)] for m in u.members])
+            else:
+                k0 = self.k0[self.runners.index(u)]
+                u.launch(self.weights[k0:k0 + u.K], self.sums[k0:k0 + u.K], eng.flat_grad)
         lv = self._loss_view()
         torch.mul(self.sums, self.inv_counts, out=lv[:self.K])
         if self.mode == "mean":

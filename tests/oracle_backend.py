@@ -54,9 +54,14 @@ class OracleBackend:
         dparams.add_(torch.from_numpy(dp).to(dparams.dtype))
 
     def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
-                         point_major=False):
+                         point_major=False, jet_offset=0, jet_stride=0):
         self.calls.append(("resid", int(x.shape[0])))
         prog.struct()   # exercises the limits / ctypes packing the CUDA backend relies on
+        n = int(x.shape[0])
+        if jet_stride:     # batched conditions: this launch works on a slice of longer jet blocks
+            jets = [j[:, jet_offset:jet_offset + n] for j in jets]
+            if djets is not None:
+                djets = [None if t is None else t[:, jet_offset:jet_offset + n] for t in djets]
         vals, sm, dj = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
                                    self._np(x), [self._np(j) for j in jets],
                                    None if weights is None else self._np(weights), want_seeds=djets is not None)

@@ -293,3 +293,22 @@ def test_program_struct_roundtrip_and_limits():
 
     with pytest.raises(trace.TraceError):
         _trace(long, model2)
+
+
+def test_same_order_conditions_share_one_forward_and_reverse_launch(oracle_backend):
+    """poisson: the four value-only Dirichlet conditions are batched -- 2 forward, 5 residual, 2 reverse launches per
+    step instead of 5 / 5 / 5 -- and the numbers stay those of the reference."""
+    g = load("poisson_2D_1C")
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    tr = mp.TrainerOneBatch(pinn, torch.optim.SGD(model.parameters(), lr=0.0), None, num_epochs=1,
+                            update_grid_every=10**9)
+    fs = tr.fused_step()
+    assert [type(u).__name__ for u in fs.units] == ["ConditionRunner", "BatchedGroup"]
+    oracle_backend.calls.clear()
+    pinn.select_batch(0)
+    tr._train_batches()
+    kinds = [c[0] for c in oracle_backend.calls]
+    assert kinds.count("fwd") == 2 and kinds.count("bwd") == 2 and kinds.count("resid") == 5
+    assert [c[2] for c in oracle_backend.calls if c[0] == "fwd"] == [96, 64]
+    assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_f64"]) < 1e-5
+    assert relerr(model.jet_engine.flat_grad.numpy(), g["grad_f64"]) < 1e-5

@@ -98,6 +98,8 @@ int mpinn_engine_supports(const mpinn_op_t* ops_host, int n_ops, int d, int orde
  *   mode 2: the same product as BF16x3 (three bf16 pieces per operand, six piece products), K-major (reverse pass)
  *   mode 3: c[128][64] = stacked(a)^T b with a, b [128][64], BF16x3, MN-major operands; rows 0..63 plus rows
  *           64..127 of c give a^T b (weight-gradient GEMM of the reverse pass)
+ *   mode 4: the same product with the two leading b pieces N-stacked: c[128][128], the four 64 x 64 quadrants add up
+ *           to a^T b (the weight-gradient GEMM when at most four jet channels leave 128 accumulator columns free)
  * (mode 1, an MN-major TF32 variant, was removed: it needs a swizzle layout the kernels do not use.) */
 int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream);
 

@@ -409,7 +409,7 @@ int mpinn_adam_step_dev(float* params, const float* grads, float* exp_avg, float
 
 int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream) {
   if (!a || !b || !c) return fail("null pointer");
-  if (mode != 0 && mode != 2 && mode != 3) return fail("mode must be 0, 2 or 3");
+  if (mode != 0 && mode != 2 && mode != 3 && mode != 4) return fail("mode must be 0, 2, 3 or 4");
   cudaError_t e = launch_umma_selftest(mode, a, b, c, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("selftest_umma", e);
   return 0;

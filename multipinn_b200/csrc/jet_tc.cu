@@ -67,6 +67,7 @@ cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* pack
 // mode 0: C[128][64] = A[128][64] * B[64][64]^T               3xTF32, K-major operands
 // mode 2: same product, BF16x3 K-major operands
 // mode 3: C[128][64] = stacked(A)^T B, A,B [128][64]          BF16x3 MN-major operands (host adds halves)
+// mode 4: C[128][128] = the same product with N-stacked B pieces (host adds the four quadrants)
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ B, float* __restrict__ C) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
-  if (t < 32) tmem_alloc(&tmem_base_s, 64);
+  if (t < 32) tmem_alloc(&tmem_base_s, 128);
   if (mode >= 2) {
     // bf16x3 staging: A [128][64] -> regions [A1][A2][A3][ZERO]; B [64 or 128][64] -> [B1][B2][B3]
     for (int i = t; i < 128 * 32; i += 128) {
@@ -132,21 +133,23 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   if (t == 0) {
     if (mode == 0) issue_gemm_kmajor(tmem, smem_u32(a_tile), smem_u32(b_tile));
     else if (mode == 2) issue_bf16x3_kmajor(tmem, smem_u32(a_tile), smem_u32(b_tile));
-    else issue_bf16x3_mnmajor(tmem, smem_u32(a_tile), smem_u32(b_tile), 0);
+    else if (mode == 3) issue_bf16x3_mnmajor(tmem, smem_u32(a_tile), smem_u32(b_tile), 0);
+    else issue_bf16x3_mnmajor_wide(tmem, smem_u32(a_tile), smem_u32(b_tile), 0);
     mma_commit(&bar);
   }
   mbar_wait(&bar, 0);
   tc_fence_after_sync();
   const int warp = t / 32;
-  for (int half = 0; half < 2; ++half) {
+  const int ncol = mode == 4 ? 128 : 64;
+  for (int part = 0; part < ncol / 32; ++part) {
     float v[32];
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, v);
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + part * 32, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) C[t * 64 + half * 32 + i] = v[i];
+    for (int i = 0; i < 32; ++i) C[t * ncol + part * 32 + i] = v[i];
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (t < 32) tmem_dealloc(tmem, 64);
+  if (t < 32) tmem_dealloc(tmem, 128);
 }
 
 cudaError_t launch_umma_selftest(int mode, const float* A, const float* B, float* C, cudaStream_t stream) {

@@ -63,9 +63,11 @@ static __device__ __noinline__ void issue_input_gradient_gemm(uint32_t d_tmem) {
   uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
   issue_bf16x3_kmajor(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kW));
 }
+template <bool WIDE>   // WIDE: 128 accumulator columns, N-stacked H pieces (see issue_bf16x3_mnmajor_wide)
 static __device__ __noinline__ void issue_weight_gradient_gemm(uint32_t d_tmem, uint32_t accumulate) {
   uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
-  issue_bf16x3_mnmajor(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kH), accumulate);
+  if (WIDE) issue_bf16x3_mnmajor_wide(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kH), accumulate);
+  else issue_bf16x3_mnmajor(d_tmem, smem_u32(smem + TcBwdSmem::kZ), smem_u32(smem + TcBwdSmem::kH), accumulate);
 }
 
 // one thread asks the L2 to fetch `bytes` (multiple of 16) starting at p
@@ -129,13 +131,17 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
   constexpr int J = jet_count(D, ORDER);
   constexpr bool LAP = (ORDER == 3);   // one second-order channel L = sum_i c_i d2/dx_i2 at jet index 1 + D
   constexpr bool HAS_SKIP = (FEAT == 1), HAS_FOURIER = (FEAT == 2);
-  constexpr uint32_t kDwCol = 448;  // TMEM columns of the dW accumulator
-  constexpr uint32_t kT0Col = 320;  // TMEM columns caching the activation value of the layer below (J <= 5)
-  constexpr uint32_t kT3Col = 384;  // TMEM columns caching its third derivative
+  // tensor-memory map: [0, 64 J) abar channels | s0 cache | s3 cache | dW accumulator.  With at most four channels
+  // the accumulator gets 128 columns and the weight-gradient GEMM runs with N-stacked operand pieces (DW_WIDE).
+  constexpr bool DW_WIDE = (J <= 4);
+  constexpr uint32_t kDwCol = DW_WIDE ? 384 : 448;  // TMEM columns of the dW accumulator
+  constexpr uint32_t kT0Col = DW_WIDE ? 256 : 320;  // TMEM columns caching the activation value of the layer below (J <= 5)
+  constexpr uint32_t kT3Col = kT0Col + 64;          // TMEM columns caching its third derivative
   // TCACHE: five channels leave 128 TMEM columns free, used to cache s0/s3 of the layer below (s1/s2 in
   // shared memory).  With seven channels TMEM is full: shared memory then holds the two basis values of
   // the activation instead and s0..s3 are re-derived from them (a few FMAs + one z0 reload) where needed.
   constexpr bool TCACHE = (J * kTcW <= (int)kT0Col);
+  static_assert(kT3Col + 64 <= kDwCol && kDwCol + (DW_WIDE ? 128 : 64) <= 512, "tensor-memory map");
   constexpr int NC = kFpt / 8;      // 8-feature chunks per thread
   uint8_t* smem = align_smem_1024(mpinn_bwd_smem_raw);
   uint8_t* z_tile = smem + TcBwdSmem::kZ;
@@ -562,7 +568,7 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           mma_commit(&mma_bar);
         } else if (t == 32) {    // ... one lane of warp 1 the weight-gradient GEMM (independent accumulators)
           tc_fence_after_sync();
-          issue_weight_gradient_gemm(tmem + kDwCol, dw_acc);
+          issue_weight_gradient_gemm<DW_WIDE>(tmem + kDwCol, dw_acc);
           mma_commit(&mma_bar);
         }
         TC_TIME(6);     // MMA issue (thread 0 only)
@@ -602,6 +608,12 @@ jet_bwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         for (int c = 0; c < NC; ++c) {
           float v[8];
           tmem_ld8(tmem + lane_base + kDwCol + f0 + c * 8, v);
+          if (DW_WIDE) {   // second column block: the H2 products of the same (out, in) features
+            float v2[8];
+            tmem_ld8(tmem + lane_base + kDwCol + 64 + f0 + c * 8, v2);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += v2[e];
+          }
           if (vec_ok) {
             red_add_v4(dst + c * 8, v[0], v[1], v[2], v[3]);
             red_add_v4(dst + c * 8 + 4, v[4], v[5], v[6], v[7]);

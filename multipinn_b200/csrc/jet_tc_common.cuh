@@ -154,6 +154,45 @@ __device__ __forceinline__ void issue_bf16x3_mnmajor(uint32_t d_tmem, uint32_t z
   }
 }
 
+// The same product with the two leading H pieces N-stacked: ONE M128 N128 group computes Z1^T H1 | Z1^T H2 (rows 0..63)
+// and Z2^T H1 | Z2^T H2 (rows 64..127) -- four piece products for 8 KB of shared-memory operands per MMA instead of
+// two groups at 6 KB each -- into 128 accumulator columns; the two small products go to the first 64 columns:
+//   cols 0..63  : rows 0..63  Z1^T H1 + Z1^T H3 + Z3^T H1      rows 64..127  Z2^T H1 (+ Z3^T H3, negligible)
+//   cols 64..127: rows 0..63  Z1^T H2                           rows 64..127  Z2^T H2
+// The caller adds the four quadrants.  In a layer's first phase (accumulate_first == 0) the wide group goes first: it
+// is the one MMA sequence that touches all 128 columns, so it carries the "overwrite" flag; in the other phases the
+// two small products go first (the tensor core truncates when it adds into the accumulator).
+__device__ __forceinline__ void issue_bf16x3_mnmajor_wide(uint32_t d_tmem, uint32_t z_tile, uint32_t h_tile,
+                                                          uint32_t accumulate_first) {
+  constexpr uint32_t idesc_w = make_idesc_bf16(128, 128, 1, 1);
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+  const uint64_t z1 = make_desc_sw128(z_tile, 1 * kBfRegion, 1024);   // (Z1 ; Z2)
+  const uint64_t z2 = make_desc_sw128(z_tile, 2 * kBfRegion, 1024);   // (Z1 ; Z3)
+  const uint64_t h0 = make_desc_sw128(h_tile, kBfRegion, 1024);       // N halves one region apart: [H1 | H2]
+  auto wide = [&](uint32_t acc) {
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      mma_bf16_ss(d_tmem, z1 + ((ks * 2048) >> 4), h0 + ((ks * 2048) >> 4), idesc_w, acc);
+      acc = 1;
+    }
+  };
+  auto small = [&]() {
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)      // (Z3 ; 0)^T H1
+      mma_bf16_ss(d_tmem, z1 + ((2 * kBfRegion + ks * 2048) >> 4), h0 + ((ks * 2048) >> 4), idesc, 1);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)      // (Z1 ; Z3)^T H3
+      mma_bf16_ss(d_tmem, z2 + ((ks * 2048) >> 4), h0 + ((2 * kBfRegion + ks * 2048) >> 4), idesc, 1);
+  };
+  if (accumulate_first == 0) {
+    wide(0);
+    small();
+  } else {
+    small();
+    wide(1);
+  }
+}
+
 // compile-time loop: f(IC<I>{}) for I in [I0, N)
 template <int I>
 struct IC {

@@ -347,24 +347,28 @@ def test_full_size_properties_poisson_1M():
 
 
 # ------------------------------------------------------------------------------ tensor-core conventions
-@pytest.mark.parametrize("mode,label", [(0, "3xTF32 K-major"), (2, "BF16x3 K-major"), (3, "BF16x3 MN-major stacked")])
+@pytest.mark.parametrize("mode,label", [(0, "3xTF32 K-major"), (2, "BF16x3 K-major"), (3, "BF16x3 MN-major stacked"),
+                                        (4, "BF16x3 MN-major, M- and N-stacked")])
 def test_umma_selftest(cuda_backend, mode, label):
     """The descriptor / swizzle / instruction-descriptor conventions of the tcgen05 engine, in isolation:
     one 128x64x64 (or 128x64x128) product through the same issue helpers the jet kernels use."""
     torch.manual_seed(mode)
+    mn = mode in (3, 4)
     a = torch.randn(128, 64, device="cuda")
-    b = torch.randn(64 if mode != 3 else 128, 64, device="cuda")
-    c = torch.zeros(128, 64, device="cuda")
+    b = torch.randn(128 if mn else 64, 64, device="cuda")
+    c = torch.zeros(128, 128 if mode == 4 else 64, device="cuda")
     cuda_backend.selftest_umma(mode, a, b, c)
     torch.cuda.synchronize()
-    if mode == 3:
+    if mn:
         ref = a.double().t() @ b.double()
         got = c[:64].double() + c[64:].double()
+        if mode == 4:
+            got = got[:, :64] + got[:, 64:]
     else:
         ref = a.double() @ b.double().t()
         got = c.double()
     err = float((got - ref).abs().max() / ref.abs().max())
-    fp32 = float(((a @ b.t() if mode != 3 else a.t() @ b).double() - ref).abs().max() / ref.abs().max())
+    fp32 = float(((a.t() @ b if mn else a @ b.t()).double() - ref).abs().max() / ref.abs().max())
     print(f"{label}: rel err {err:.2e} (cuBLAS fp32 {fp32:.2e})")
     assert err < 1e-6
 

@@ -449,7 +449,14 @@ def run_ours(args):
                         "fwd_avg_launch_ms": fwd_ms, "residual_program_avg_launch_ms": res_ms,
                         "fwd_achieved": (n_domain * J_ref * 2 * Pw / (fwd_ms * 1e-3) / 1e12) if fwd_ms else None,
                         "fwd_traffic": ncu_traffic(args.workload, n_domain, "fwd"),
-                        "our_kernels_ms_per_step_unfused_launches": kernel_ms_per_step}
+                        "our_kernels_ms_per_step_unfused_launches": kernel_ms_per_step,
+                        # the ALGORITHM needs only the points twice and the parameters / gradients;
+                        # the pre-activation stash between the forward and the reverse kernel is this design's
+                        # traffic, ~1000x that (stash_bytes_per_launch written once and read once)
+                        "algorithmic_hbm_bytes_per_step": sum(len(p) for p in dev_pts) * din * 4 * 2
+                        + 3 * sum(p.numel() for p in model.parameters()) * 4}
+            tr_b, tr_f = roofline["traffic"], roofline["fwd_traffic"]
+            roofline["measured_dram_bytes_domain_fwd_plus_bwd"] = (tr_b + tr_f) if (tr_b and tr_f) else None
         step_flops = 0
         for i in range(len(spec)):
             if programs[i] is not None:

@@ -277,9 +277,13 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   int rc = 0;
   const bool tc = use_tc(prog, d, order, engine, false, &rc);
   if (rc) return rc;
-  if (tc && stash == nullptr && engine == MPINN_ENGINE_TCGEN05)
-    return fail("the tcgen05 engine needs a stash buffer (pass mpinn_stash_bytes() bytes, also for inference)");
-  if (tc && stash != nullptr) {
+  // stash == NULL is a value-only pass.  The tcgen05 engine runs it without writing anything for a reverse pass,
+  // except for programs with skip connections, whose per-CTA skip scratch lives behind the stash.
+  const bool tc_ok = tc && (stash != nullptr || !prog.has_skip);
+  if (tc && !tc_ok && engine == MPINN_ENGINE_TCGEN05)
+    return fail("the tcgen05 engine needs a stash buffer for programs with skip connections "
+                "(pass mpinn_stash_bytes() bytes, also for inference)");
+  if (tc_ok) {
     e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
                       info.sm_count, (cudaStream_t)stream);
   } else {

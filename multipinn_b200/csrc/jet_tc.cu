@@ -244,6 +244,9 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
     float xv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
+    // stash == nullptr: value-only / inference pass, nothing is kept for a reverse pass (programs with skip
+    // connections still need the buffer: their skip scratch lives behind it)
+    const bool keep = stash != nullptr;
     float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;   // [plane][128 points]
     // jets travelling along a skip connection: this CTA's [channel][feature][point] scratch (L2 resident)
     float* skip_s = stash + (int64_t)prog.total_planes * n_pad + (int64_t)blockIdx.x * (J * kTcW * 128) + p;
@@ -326,7 +329,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int ff = c * 8 + e;
-            zst[(j * kTcW + f0 + ff) * 128] = z[e];          // stash for the reverse pass
+            if (keep) zst[(j * kTcW + f0 + ff) * 128] = z[e];          // stash for the reverse pass
             if (kind == 0) {
               float c0, c1, c2, c3;
               act_coeffs<false>(act_src, z[e], c0, c1, c2, c3);
@@ -442,7 +445,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
             for (int j = 0; j < J; ++j) z[j] += skip_s[(j * kTcW + f) * 128];
           }
 #pragma unroll
-          for (int j = 0; j < J; ++j) zst[(j * kTcW + f) * 128] = z[j];
+          if (keep) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) zst[(j * kTcW + f) * 128] = z[j];
+          }
           act_jets<D, ORDER>(sv.act, z, prog.lap_c);   // (the last hidden layer is never the Fourier op)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -544,7 +550,7 @@ static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, con
 cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float* packed, const float* x,
                           int64_t n, int d, int order, float* out, float* stash, int64_t n_pad,
                           int sm_count, cudaStream_t stream) {
-  if (stash == nullptr) return cudaErrorInvalidValue;  // this engine always runs through the stash
+  if (stash == nullptr && prog.has_skip) return cudaErrorInvalidValue;  // the skip scratch lives behind the stash
   const int feat = tc_feat(prog);
 #define TC_FWD(D_, O_)                                                                                      \
   if (d == D_ && order == O_) {                                                                             \

@@ -212,6 +212,7 @@ class JetEngine:
         self._params = []
         self._offsets = []
         self._tc_ok = {}
+        self.has_skip = bool((self.ops[:, 6] != 0).any())
 
     # ---------------------------------------------------------------- flat buffers
     def _is_flat(self) -> bool:
@@ -321,10 +322,10 @@ class JetEngine:
         n, d = x.shape
         if out is None:
             out = torch.empty((self.n_jets(order), n, self.n_out), dtype=torch.float32, device=x.device)
-        if stash is None and (need_stash or (x.is_cuda and self.kernel_engine != _lib.ENGINE_FFMA
+        if stash is None and (need_stash or (x.is_cuda and self.has_skip and self.kernel_engine != _lib.ENGINE_FFMA
                                              and self.tc_supported(order))):
-            # the tensor-core engine always round-trips pre-activations through this buffer, also for a
-            # value-only pass; programs only the FP32-FMA engine runs need no stash for inference
+            # a value-only pass needs no stash, except for residual-block programs on the tensor-core engine:
+            # the jets travelling along a skip connection use a per-CTA scratch behind it
             stash = torch.empty(self.stash_floats(order, n), dtype=torch.float32, device=x.device)
         b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine,
                       **({"lap": lap} if lap is not None else {}))

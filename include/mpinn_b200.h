@@ -105,8 +105,9 @@ int mpinn_engine_supports(const mpinn_op_t* ops_host, int n_ops, int d, int orde
 int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void* stream);
 
 /* Diagnostic: when the library is built with -DMPINN_TC_TIMING=1 the tcgen05 reverse kernel accumulates
- * clock64() deltas per code segment (CTA 0, threads 0 and 224: 2 x 16 counters); this synchronises the
- * device, copies up to 32 counters to out_host and clears them.  All zeros in a normal build. */
+ * clock64() deltas per code segment (CTA 0, threads 0 and 224: 2 x 16 counters), and so does the forward kernel
+ * (counters 32..63); this synchronises the device, copies up to n <= 64 counters to out_host and clears them.
+ * All zeros in a normal build. */
 int mpinn_debug_counters(long long* out_host, int n);
 
 /* sum_i r[i*stride]^2 added into *accum (device scalar).

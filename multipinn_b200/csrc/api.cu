@@ -30,6 +30,7 @@ int64_t tc_block_floats(int width);
 cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* packed,
                            cudaStream_t stream);
 cudaError_t read_tc_debug(long long* out, int n);
+cudaError_t read_tc_debug_fwd(long long* out, int n);
 // residual.cu
 cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
@@ -422,6 +423,7 @@ int mpinn_selftest_umma(int mode, const float* a, const float* b, float* c, void
 int mpinn_debug_counters(long long* out_host, int n) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = read_tc_debug(out_host, n);
+  if (e == cudaSuccess && n > 32) e = read_tc_debug_fwd(out_host + 32, n - 32);   // forward kernel: counters 32..63
   if (e != cudaSuccess) return fail_cuda("debug_counters", e);
   return 0;
 }

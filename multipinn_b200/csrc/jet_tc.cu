@@ -18,6 +18,35 @@ namespace mpinn {
 
 int64_t tc_block_floats(int width) { return width == kTcW ? kTcBlockFloats : 0; }
 
+// optional cycle accounting of the forward kernel (build with -DMPINN_TC_TIMING=1, see jet_tc_bwd.cu): CTA 0,
+// threads 0 and 224 accumulate clock64() deltas per code segment; mpinn_debug_counters() returns them as
+// counters 32..63.
+#ifndef MPINN_TC_TIMING
+#define MPINN_TC_TIMING 0
+#endif
+__device__ long long g_tc_dbg_fwd[2][16];
+#if MPINN_TC_TIMING
+#define TCF_TIME(slot)                                                  \
+  do {                                                                  \
+    if (blockIdx.x == 0 && (t == 0 || t == 224)) {                      \
+      const long long now_ = clock64();                                 \
+      g_tc_dbg_fwd[t == 0 ? 0 : 1][slot] += now_ - dbg_last;            \
+      dbg_last = now_;                                                  \
+    }                                                                   \
+  } while (0)
+#else
+#define TCF_TIME(slot) do {} while (0)
+#endif
+
+cudaError_t read_tc_debug_fwd(long long* out, int n) {
+  long long h[32];
+  cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_dbg_fwd, sizeof(h));
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+  long long z[32] = {0};
+  return cudaMemcpyToSymbol(g_tc_dbg_fwd, z, sizeof(z));
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight packing: global image of the swizzled shared-memory operand tiles
 // ---------------------------------------------------------------------------------------------
@@ -238,12 +267,16 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #define BLK(j) ((blk_p >> (4 * (j))) & 7u)
   uint32_t free_mask = 0xFFu;
 
+#if MPINN_TC_TIMING
+  long long dbg_last = clock64();
+#endif
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t pt = (int64_t)tile * 128 + p;
     const bool valid = pt < n;
     float xv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
+    TCF_TIME(15);
     // stash == nullptr: value-only / inference pass, nothing is kept for a reverse pass (programs with skip
     // connections still need the buffer: their skip scratch lives behind it)
     const bool keep = stash != nullptr;
@@ -270,6 +303,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
         }
       }
       if (t < kTcW) bias_s[(ST_B ^ 1) * kTcW + t] = __ldg(params + op.b_off + t);   // read one stage later
+      TCF_TIME(10);   // layer start: weight prefetch issue, bias staging
       const int act_src = HAS_FOURIER ? act_of(sv, f0) : sv.act;
       float s1[kFpt], s2[kFpt], zi_keep[kFpt];
       float* zst = tstash + sv.stash_plane * 128;
@@ -358,8 +392,10 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
           for (int e = 0; e < 8; ++e) split_tf32(a[e], hi[e], lo[e]);
           if (c == 0) {   // the GEMM issued two channels ago still reads this buffer
+            TCF_TIME(11);   // source jets + activation math + stash stores + split, first chunk
             if (buf == 0 && pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
             if (buf == 1 && pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
+            TCF_TIME(12);   // wait for the A buffer
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -369,9 +405,11 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
                 make_float4(lo[h * 4], lo[h * 4 + 1], lo[h * 4 + 2], lo[h * 4 + 3]);
           }
         }
+        TCF_TIME(13);     // rest of the channel's staging (second chunk, tile stores)
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
+        TCF_TIME(14);     // channel barrier
         // blocks of the source layer that nobody needs any more
         if (S >= 1) {
           if (kind == 0) free_mask |= 1u << BLK(0);
@@ -390,6 +428,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
           issue_gemm_kmajor(tmem + nb * kTcW, smem_u32(at), smem_u32(smem + TcSmem::kW + ST_W * kWTileBytes));
           mma_commit(&mma_bar[buf]);
         }
+        TCF_TIME(6);      // MMA issue (thread 0 only)
         if (buf == 0) pending0 = 1; else pending1 = 1;
       };
       if constexpr (J <= 5) {
@@ -408,6 +447,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       }
       if (pending0) { mbar_wait(&mma_bar[0], bar_phase0); bar_phase0 ^= 1; pending0 = 0; }
       if (pending1) { mbar_wait(&mma_bar[1], bar_phase1); bar_phase1 ^= 1; pending1 = 0; }
+      TCF_TIME(7);        // layer-end GEMM wait
       tc_fence_after_sync();
       blk_p = nblk_p;
       nblk_p = 0;
@@ -494,6 +534,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
       __syncthreads();
       tc_fence_after_sync();
       st ^= 1u;
+      TCF_TIME(9);        // output op
     }
   }
   tc_fence_before_sync();

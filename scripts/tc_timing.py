@@ -28,15 +28,17 @@ for th, label in ((0, "thread 0 (issuer)"), (1, "thread 224")):
         print(f"   {nm:40s} {vals[k]:12d}  {100*vals[k]/max(tot,1):5.1f}%   per tile-layer {vals[k]/8/8:9.0f}")
 
 # ---- forward
-lib.mpinn_debug_counters(buf, 32)
+buf = (ctypes.c_longlong * 64)()
+lib.mpinn_debug_counters(buf, 64)
 out, stash = e.forward(x, ORDER, True, lap=LAP)
-lib.mpinn_debug_counters(buf, 32)
-names = {15: "tile start", 10: "layer: W tile load", 11: "channel: source + activation math chunk0", 12: "channel: wait A buffer",
-         13: "channel: rest of staging", 14: "channel: barrier", 6: "channel: MMA issue", 7: "layer: end GEMM wait", 9: "output op"}
+lib.mpinn_debug_counters(buf, 64)
+names = {15: "tile start", 10: "layer start (W prefetch, bias)", 11: "channel: source + activation math + stash, chunk 0",
+         12: "channel: wait A buffer", 13: "channel: rest of staging", 14: "channel: barrier", 6: "channel: MMA issue",
+         7: "layer: end GEMM wait", 9: "output op"}
 print("FORWARD")
 for th, label in ((0, "thread 0 (issuer)"), (1, "thread 224")):
-    vals = [buf[th * 16 + i] for i in range(16)]
+    vals = [buf[32 + th * 16 + i] for i in range(16)]
     tot = sum(vals)
     print(label, "total cycles", tot, " per tile", tot / 8)
     for k, nm in names.items():
-        print(f"   {nm:45s} {vals[k]:12d}  {100*vals[k]/max(tot,1):5.1f}%   per tile-layer {vals[k]/8/8:9.0f}")
+        print(f"   {nm:52s} {vals[k]:12d}  {100*vals[k]/max(tot,1):5.1f}%   per tile-layer {vals[k]/8/8:9.0f}")

@@ -151,9 +151,13 @@ class BatchedGroup:
 class FusedStep:
     """Whole-step executor for a trainer whose conditions are all traced."""
 
-    def __init__(self, engine, conditions, programs, mode: str, flat_adam=None, use_graphs: bool = True):
+    def __init__(self, engine, conditions, programs, mode: str, flat_adam=None, use_graphs: bool = True, reg=None):
         self.engine = engine
-        self.mode = mode                 # "mean" | "legacy"
+        # loss policy: "mean" | "legacy" (the reference's two built-in ones) | "constant" (ConstantLosses) |
+        # "gradient" / "normal" (GradientLosses / NormalLosses: statistics of K per-condition gradients)
+        self.mode = mode
+        self.reg = reg
+        self.per_condition = mode in ("gradient", "normal")
         self.flat_adam = flat_adam
         self.runners: List[ConditionRunner] = [ConditionRunner(c, p, engine) for c, p in zip(conditions, programs)]
         self.K = sum(r.K for r in self.runners)
@@ -163,10 +167,9 @@ class FusedStep:
             self.k0.append(k)
             k += r.K
         # launch units, in condition order of their first member: single conditions or batched groups
-        self.batch_conditions = True
         by_key, self.units = {}, []
         for r in self.runners:
-            key = r.batch_key()
+            key = None if self.per_condition else r.batch_key()   # per-condition gradients: one reverse launch each
             if key is None:
                 self.units.append(r)
             elif key in by_key:
@@ -192,11 +195,16 @@ class FusedStep:
         eng = trainer._engine
         if eng is None or eng.points_grad or trainer.num_batches < 1:
             return None
+        from .regularization import ConstantLosses, GradientLosses, NormalLosses
         from .trainer.trainer import Trainer
+        reg = None
         if trainer.calc_loss == Trainer.mean_calc_loss:
             mode = "mean"
         elif trainer.calc_loss == Trainer.sum_of_means_calc_loss:
             mode = "legacy"
+        elif type(trainer.calc_loss) in (ConstantLosses, GradientLosses, NormalLosses):
+            reg = trainer.calc_loss
+            mode = {ConstantLosses: "constant", GradientLosses: "gradient", NormalLosses: "normal"}[type(reg)]
         else:
             return None
         progs = []
@@ -205,10 +213,16 @@ class FusedStep:
             if p is None:
                 return None
             progs.append(p)
-        if sum(len(p.outputs) for p in progs) + 1 > eng.COMM_TAIL:
+        K = sum(len(p.outputs) for p in progs)
+        if K + 1 > eng.COMM_TAIL:
+            return None
+        # the regularizers raise the reference's own exceptions for shapes they do not support: leave those to them
+        if mode == "constant" and len(reg.lambdas) != K:
+            return None
+        if mode in ("gradient", "normal") and (K != len(progs) or K < 2):
             return None
         return FusedStep(eng, trainer.pinn.conditions, progs, mode, trainer._flat_adam,
-                         use_graphs=getattr(trainer, "use_cuda_graphs", True))
+                         use_graphs=getattr(trainer, "use_cuda_graphs", True), reg=reg)
 
     # ------------------------------------------------------------------ buffers
     def _bind(self, device):
@@ -235,8 +249,27 @@ class FusedStep:
             self.inv_total = 1.0 / total
             if self.mode == "mean":      # total = sum_k sum_n r^2 / sum_k N_k   (reference PINN.py:109-125)
                 self.weights = torch.full((K,), 1.0 / total, dtype=torch.float32, device=device)
+            elif self.mode == "constant":  # total = sum_k lambda_k mean_n r^2     (reference regularization/constant.py)
+                self.lambdas = torch.tensor([float(v) for v in self.reg.lambdas], dtype=torch.float32, device=device)
+                self.weights = self.inv_counts * self.lambdas
             else:                        # total = sum_k mean_n r^2                (reference trainer.py:155-167)
-                self.weights = self.inv_counts.clone()
+                self.weights = self.inv_counts.clone()  # (gradient / normal: per-condition means, combined below)
+            if self.per_condition:
+                P = eng.flat_grad.numel()
+                self.G = torch.zeros((K, P), dtype=torch.float32, device=device)   # one gradient slab per condition
+                if self.reg.lambda_regularization is None or self.reg.lambda_regularization.device != device:
+                    self.reg.lambda_regularization = torch.ones(K - 1, dtype=torch.float32, device=device)
+                if self.mode == "gradient":
+                    # w_i = 1 / (T * numel(tensor(i))): sum_i |g_i| w_i == mean over tensors of mean |g|
+                    w = torch.zeros(P, dtype=torch.float32, device=device)
+                    trainable = [(p, off) for p, off in zip(eng._params, eng._offsets) if p.requires_grad]
+                    for p, off in trainable:
+                        w[off:off + p.numel()] = 1.0 / (len(trainable) * p.numel())
+                    self.tensor_mean_w = w
+                else:
+                    last = list(list(eng.model.children())[-1].children())[-1]
+                    off = next(o for p, o in zip(eng._params, eng._offsets) if p is last.weight)
+                    self.last_slice = slice(off, off + last.weight.numel())
             if self.flat_adam is not None:
                 self.adam_state = torch.zeros(4, dtype=torch.float32, device=device)
                 self.adam_state[1] = float(self.flat_adam.step)
@@ -253,18 +286,39 @@ class FusedStep:
         eng = self.engine
         eng.flat_grad.zero_()
         self.sums.zero_()
+        if self.per_condition:
+            self.G.zero_()
         for u in self.units:
             if isinstance(u, BatchedGroup):
                 u.launch(self.weights, self.sums, eng.flat_grad, [self.k0[self.runners.index(m)] for m in u.members])
             else:
-                k0 = self.k0[self.runners.index(u)]
-                u.launch(self.weights[k0:k0 + u.K], self.sums[k0:k0 + u.K], eng.flat_grad)
+                c = self.runners.index(u)
+                k0 = self.k0[c]
+                u.launch(self.weights[k0:k0 + u.K], self.sums[k0:k0 + u.K],
+                         self.G[c] if self.per_condition else eng.flat_grad)
         lv = self._loss_view()
-        torch.mul(self.sums, self.inv_counts, out=lv[:self.K])
+        K = self.K
+        if self.mode == "constant":      # reported losses are the weighted ones (reference constant.py:33-36)
+            torch.mul(self.sums, self.weights, out=lv[:K])
+            torch.sum(lv[:K], dim=0, out=lv[K])
+            return
+        torch.mul(self.sums, self.inv_counts, out=lv[:K])
         if self.mode == "mean":
-            torch.mul(torch.sum(self.sums), self.inv_total, out=lv[self.K])
+            torch.mul(torch.sum(self.sums), self.inv_total, out=lv[K])
+        elif self.mode == "legacy":
+            torch.sum(lv[:K], dim=0, out=lv[K])
         else:
-            torch.sum(lv[:self.K], dim=0, out=lv[self.K])
+            # GradientLosses (reference gradient.py:35-59):  lambda_k <- (1-a) lambda_k + a max|g_0| / mean-of-means|g_k|
+            # NormalLosses   (reference normal.py:27-45):    lambda_k <- (1-a) lambda_k + a std(g_0[W_last]) / std(g_k[W_last])
+            # then  total = L_0 + sum_k lambda_k L_k  and its gradient  g_0 + sum_k lambda_k g_k
+            G, lam, a = self.G, self.reg.lambda_regularization, float(self.reg.alpha)
+            if self.mode == "gradient":
+                ratio = G[0].abs().max() / (G[1:].abs() * self.tensor_mean_w).sum(dim=1)
+            else:
+                ratio = torch.std(G[0, self.last_slice]) / torch.std(G[1:, self.last_slice], dim=1)
+            lam.mul_(1.0 - a).add_(ratio, alpha=a)
+            torch.add(G[0], torch.mv(G[1:].t(), lam), out=eng.flat_grad)
+            torch.add(lv[0], torch.dot(lam, lv[1:K]), out=lv[K])
 
     def _update(self, grad_scale: float):
         eng = self.engine

@@ -34,8 +34,11 @@ _TABLE: Dict[str, Dict[str, Tuple[str, str]]] = {
         "ResNet": ("multipinn_b200.neural_network.residual_neural_network", "ResNet")},
     "multipinn.neural_network.fourier_features": {
         n: ("multipinn_b200.neural_network.fourier_features", n) for n in ("FourierEncoding", "FourierFeatureNetwork")},
+    "multipinn.neural_network.inference_wrapper": {
+        "Inference": ("multipinn_b200.neural_network.inference_wrapper", "Inference")},
     "multipinn.neural_network": {
-        **{n: ("multipinn_b200.neural_network", n) for n in ("FNN", "XavierFNN", "ResNet", "FourierFeatureNetwork")},
+        **{n: ("multipinn_b200.neural_network", n) for n in ("FNN", "XavierFNN", "ResNet", "FourierFeatureNetwork",
+                                                             "Inference")},
         "FFNN": ("multipinn_b200.neural_network", "FourierFeatureNetwork")},
     "multipinn.condition.condition": {
         n: ("multipinn_b200.condition.condition", n) for n in ("Condition", "ConditionExtra")},

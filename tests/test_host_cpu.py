@@ -434,3 +434,42 @@ def test_frozen_layers_use_the_generic_optimizer_path(oracle_backend):
     m3, c3, p3 = build_pinn("navier_stokes_3D", g3)
     tr3 = mp.TrainerOneBatch(p3, torch.optim.Adam(m3.parameters(), lr=1e-3), None, num_epochs=1, update_grid_every=10**9)
     assert tr3._flat_adam is not None
+
+
+def test_symbols_diff_mode_generates_finite_difference_code(oracle_backend):
+    """Symbols(mode="diff") (reference condition/symbols.py:189-234): generated source, and its values against the
+    analytic jets (central second differences are accurate to ~1e-3 at eps = 2^-7)."""
+    s = mp.Symbols(variables="x, t", functions="u", mode="diff")
+    fn = s("u, u_x, u_xx, u_xt")
+    src = fn.source
+    assert "fns = model(arg)" in src and "(u,) = unpack(fns)" in src
+    assert "(u_x,) = unpack(num_diff_random(model, arg, fns, torch.Tensor([[1, 0]])))" in src
+    assert "(u_xx,) = unpack(num_diff_second_same(model, arg, fns, torch.Tensor([[1, 0]])))" in src
+    assert "(u_xt,) = unpack(num_diff_second_cross(model, arg, torch.Tensor([[1, 0]]), torch.Tensor([[0, 1]])))" in src
+    with pytest.raises(ValueError):
+        s("u_xxx")
+    with pytest.raises(ValueError):
+        mp.Symbols("x", "u", mode="nope")("u")
+    g = load("allen_cahn_2D_1C")
+    model = product_model("allen_cahn_2D_1C", g)
+    pts = torch.tensor(g["pts0"])
+    torch.manual_seed(0)
+    with torch.no_grad():
+        u, u_x, u_xx, u_xt = fn(model, pts)
+    assert relerr(u.numpy(), g["u_f64"][:, 0]) < 1e-5
+    assert relerr(u_xx.numpy(), g["d2u_f64"][:, 0, 0]) < 2e-2
+    assert relerr(u_x.numpy(), g["du_f64"][:, 0, 0]) < 5e-2
+
+
+def test_inference_wrapper(oracle_backend):
+    g = load("poisson_2D_1C")
+    model = product_model("poisson_2D_1C", g)
+    pts = torch.tensor(g["pts0"])
+    inf = mp.neural_network.Inference(model, batchsize=32)
+    with torch.no_grad():
+        y = inf(pts)
+    assert y.shape == (len(pts), 1)
+    assert relerr(y.numpy(), g["u_f64"]) < 1e-5
+    inf.launch_points = 40         # several launches stack to the same answer
+    with torch.no_grad():
+        assert torch.equal(inf(pts), y)

@@ -312,3 +312,35 @@ def test_same_order_conditions_share_one_forward_and_reverse_launch(oracle_backe
     assert [c[2] for c in oracle_backend.calls if c[0] == "fwd"] == [96, 64]
     assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_f64"]) < 1e-5
     assert relerr(model.jet_engine.flat_grad.numpy(), g["grad_f64"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["constant", "gradient", "normal"])
+def test_regularizer_policies_run_on_the_fused_step(kind, oracle_backend):
+    """ConstantLosses / GradientLosses / NormalLosses as loss policies of the fused step (K per-condition gradient
+    slabs from one reverse launch per condition, statistics and the weighted combination on the device) give the
+    eager jet path's numbers -- which tests/test_host_cpu.py pins to runs of the unmodified reference."""
+    g = load("poisson_2D_1C")
+    results = []
+    for fused in (True, False):
+        model, conds, pinn = build_pinn("poisson_2D_1C", g)
+        reg = {"constant": lambda: mp.ConstantLosses([1.0, 2.0, 3.0, 4.0, 5.0]),
+               "gradient": lambda: mp.GradientLosses(alpha=0.9), "normal": lambda: mp.NormalLosses(alpha=0.9)}[kind]()
+        tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-3), None, num_epochs=3,
+                                update_grid_every=10**9, calc_loss=reg)
+        tr.use_fused_step = fused
+        assert (tr.fused_step() is not None) == fused
+        if fused:
+            assert tr.fused_step().mode == kind
+        out = []
+        for e in range(3):
+            tr.current_epoch = e + 1
+            tr._train_epoch()
+            lam = reg.lambda_regularization.numpy().copy() if kind != "constant" else np.zeros(1)
+            out.append((float(tr.total_loss), tr.epoch_loss_detailed.numpy().copy(), lam))
+        results.append((out, model.jet_engine.flat.detach().numpy().copy()))
+    (fo, fw), (eo, ew) = results
+    for (ft, fl, flam), (et, el, elam) in zip(fo, eo):
+        assert relerr(ft, et) < 1e-6 and relerr(fl, el) < 1e-6
+        if kind != "constant":
+            assert relerr(flam, elam) < 1e-5
+    assert np.abs(fw - ew).max() < 1e-6

@@ -72,7 +72,8 @@ int mpinn_pack_params(const mpinn_op_t* ops_host, int n_ops, const float* params
  *   x    [n,d]      collocation points
  *   out  [J,n,o]    jets of the o network outputs (o = out_dim of the last op)
  *   stash           mpinn_stash_bytes() bytes, or NULL for a value-only/inference pass (nothing is written for a
- *                   reverse pass; programs with skip connections on the tcgen05 engine still need the buffer)
+ *                   reverse pass; the tcgen05 engine does this at order 0 for programs without skip connections,
+ *                   MPINN_ENGINE_AUTO otherwise runs the FP32-FMA engine)
  *   lap_coef_host   HOST pointer to the d weights c_i of the second-order channel when order == 3, else NULL */
 int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params,
                       const void* packed, const float* x, int64_t n, int d, int order,

@@ -278,12 +278,13 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   int rc = 0;
   const bool tc = use_tc(prog, d, order, engine, false, &rc);
   if (rc) return rc;
-  // stash == NULL is a value-only pass.  The tcgen05 engine runs it without writing anything for a reverse pass,
-  // except for programs with skip connections, whose per-CTA skip scratch lives behind the stash.
-  const bool tc_ok = tc && (stash != nullptr || !prog.has_skip);
+  // stash == NULL is a value-only pass.  The tcgen05 engine has a no-stash variant for order 0 (inference) of
+  // programs without skip connections (their per-CTA skip scratch lives behind the stash); otherwise ENGINE_AUTO
+  // falls to the FP32-FMA engine and an explicit tcgen05 request is refused.
+  const bool tc_ok = tc && (stash != nullptr || (order == 0 && !prog.has_skip));
   if (tc && !tc_ok && engine == MPINN_ENGINE_TCGEN05)
-    return fail("the tcgen05 engine needs a stash buffer for programs with skip connections "
-                "(pass mpinn_stash_bytes() bytes, also for inference)");
+    return fail("the tcgen05 engine runs without a stash buffer only at order 0 and without skip connections "
+                "(pass mpinn_stash_bytes() bytes)");
   if (tc_ok) {
     e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
                       info.sm_count, (cudaStream_t)stream);

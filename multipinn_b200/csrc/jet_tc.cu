@@ -203,7 +203,8 @@ struct TcSmem {
 
 // FEAT selects the program family at compile time so the plain-FNN kernel carries no extra registers:
 //   0 = plain FNN, 1 = residual blocks (SAVE_SKIP/ADD_SKIP), 2 = Fourier-feature first op
-template <int D, int ORDER, int FEAT>
+//   KEEP = false: value-only / inference pass, nothing is written for a reverse pass (instantiated for order 0)
+template <int D, int ORDER, int FEAT, bool KEEP = true>
 __global__ void __launch_bounds__(kTcThreads, 1)
 jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ params,
            const float* __restrict__ packed, const float* __restrict__ x, int64_t n,
@@ -277,9 +278,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 #pragma unroll
     for (int i = 0; i < D; ++i) xv[i] = valid ? __ldg(x + pt * D + i) : 0.0f;
     TCF_TIME(15);
-    // stash == nullptr: value-only / inference pass, nothing is kept for a reverse pass (programs with skip
-    // connections still need the buffer: their skip scratch lives behind it)
-    const bool keep = stash != nullptr;
+    constexpr bool keep = KEEP;
     float* tstash = stash + (int64_t)tile * prog.total_planes * 128 + p;   // [plane][128 points]
     // jets travelling along a skip connection: this CTA's [channel][feature][point] scratch (L2 resident)
     float* skip_s = stash + (int64_t)prog.total_planes * n_pad + (int64_t)blockIdx.x * (J * kTcW * 128) + p;
@@ -574,11 +573,11 @@ bool tc_forward_supported(const DevProg& prog, int d, int order) {
   return last.kind == MPINN_OP_LINEAR && last.in_dim == kTcW && last.act == MPINN_ACT_NONE && !last.flags;
 }
 
-template <int D, int ORDER, int FEAT>
+template <int D, int ORDER, int FEAT, bool KEEP = true>
 static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, const float* packed,
                                    const float* x, int64_t n, float* out, float* stash, int64_t n_pad,
                                    int sm_count, cudaStream_t stream) {
-  auto kern = jet_fwd_tc<D, ORDER, FEAT>;
+  auto kern = jet_fwd_tc<D, ORDER, FEAT, KEEP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal);
   if (e != cudaSuccess) return e;
   const int n_tiles = (int)((n + 127) / 128);
@@ -591,8 +590,18 @@ static cudaError_t launch_fwd_tc_t(const DevProg& prog, const float* params, con
 cudaError_t launch_fwd_tc(const DevProg& prog, const float* params, const float* packed, const float* x,
                           int64_t n, int d, int order, float* out, float* stash, int64_t n_pad,
                           int sm_count, cudaStream_t stream) {
-  if (stash == nullptr && prog.has_skip) return cudaErrorInvalidValue;  // the skip scratch lives behind the stash
   const int feat = tc_feat(prog);
+  if (stash == nullptr) {   // value-only pass: order 0, no skip connections (their scratch lives behind the stash)
+    if (order != 0 || prog.has_skip) return cudaErrorInvalidValue;
+#define TC_FWD0(D_)                                                                                             \
+  if (d == D_) {                                                                                                \
+    if (feat == 0) return launch_fwd_tc_t<D_, 0, 0, false>(prog, params, packed, x, n, out, stash, n_pad, sm_count, stream); \
+    return launch_fwd_tc_t<D_, 0, 2, false>(prog, params, packed, x, n, out, stash, n_pad, sm_count, stream);    \
+  }
+    TC_FWD0(1); TC_FWD0(2); TC_FWD0(3);
+#undef TC_FWD0
+    return cudaErrorInvalidValue;
+  }
 #define TC_FWD(D_, O_)                                                                                      \
   if (d == D_ && order == O_) {                                                                             \
     if (feat == 0) return launch_fwd_tc_t<D_, O_, 0>(prog, params, packed, x, n, out, stash, n_pad, sm_count, stream); \

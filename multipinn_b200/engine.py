@@ -322,10 +322,11 @@ class JetEngine:
         n, d = x.shape
         if out is None:
             out = torch.empty((self.n_jets(order), n, self.n_out), dtype=torch.float32, device=x.device)
-        if stash is None and (need_stash or (x.is_cuda and self.has_skip and self.kernel_engine != _lib.ENGINE_FFMA
-                                             and self.tc_supported(order))):
-            # a value-only pass needs no stash, except for residual-block programs on the tensor-core engine:
-            # the jets travelling along a skip connection use a per-CTA scratch behind it
+        if stash is None and (need_stash or (x.is_cuda and (order > 0 or self.has_skip)
+                                             and self.kernel_engine != _lib.ENGINE_FFMA and self.tc_supported(order))):
+            # inference (order 0) needs no stash on either engine; value-only passes WITH derivative channels and
+            # residual-block programs (their skip scratch lives behind it) stay on the tensor-core engine by
+            # passing one
             stash = torch.empty(self.stash_floats(order, n), dtype=torch.float32, device=x.device)
         b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine,
                       **({"lap": lap} if lap is not None else {}))

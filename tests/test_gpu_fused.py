@@ -304,27 +304,29 @@ def test_adam_device_state_matches_torch_adam(cuda_backend):
 
 # ------------------------------------------------------------------------------ C ABI corner cases
 def test_forward_without_stash_through_the_c_abi(cuda_backend):
-    """stash = NULL is a value-only pass on every engine (the tcgen05 engine then writes nothing for a reverse pass);
-    only a residual-block program on an explicit tcgen05 request is refused, with a message (never an uninitialised
-    return code): its skip scratch lives behind the stash."""
+    """stash = NULL is a value-only pass: the FP32-FMA engine runs it at any order, the tcgen05 engine at order 0
+    (inference: nothing is written for a reverse pass) for programs without skip connections; an explicit tcgen05
+    request it cannot serve is refused with a message (never an uninitialised return code)."""
     m, _, _ = full_model("poisson_2D_1C", 2)
     e = m.jet_engine
     x = torch.rand((300, 2), device="cuda")
     ref, _ = e.forward(x, 2, need_stash=True)
     ops = m.jet_program()
-    for eng_id in (_lib.ENGINE_FFMA, _lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05):
+    for eng_id in (_lib.ENGINE_FFMA, _lib.ENGINE_AUTO):
         out = torch.empty_like(ref)
         cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 2, out, None, eng_id)
         assert relerr(out.cpu().numpy(), ref.cpu().numpy()) < TOL
-    out = torch.empty_like(ref)
-    cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 2, out, None, _lib.ENGINE_TCGEN05)
-    assert torch.equal(out, ref)         # same kernel, same numbers, no stash
+    with pytest.raises(RuntimeError, match="stash"):
+        cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 2, torch.empty_like(ref), None, _lib.ENGINE_TCGEN05)
+    out = torch.empty_like(ref[:1])
+    cuda_backend.jet_forward(ops, e.flat.detach(), e.packed, x, 0, out, None, _lib.ENGINE_TCGEN05)
+    assert torch.equal(out[0], ref[0])   # the same tensor-core arithmetic, no stash
     r, _, _ = full_model("navier_stokes_2D", 2)
     xr = torch.rand((300, 2), device="cuda")
     refr, _ = r.jet_engine.forward(xr, 1, need_stash=True)
     with pytest.raises(RuntimeError, match="stash"):
-        cuda_backend.jet_forward(r.jet_program(), r.jet_engine.flat.detach(), r.jet_engine.packed, xr, 1,
-                                 torch.empty_like(refr), None, _lib.ENGINE_TCGEN05)
+        cuda_backend.jet_forward(r.jet_program(), r.jet_engine.flat.detach(), r.jet_engine.packed, xr, 0,
+                                 torch.empty_like(refr[:1]), None, _lib.ENGINE_TCGEN05)
     with torch.no_grad():                # the host allocates the scratch for residual-block inference itself
         assert torch.equal(r(xr), refr[0])
     with pytest.raises(RuntimeError, match="lap_coef"):

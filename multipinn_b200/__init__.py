@@ -7,7 +7,7 @@ All numerics run in hand-written sm_100a kernels (``csrc/``) reached through a C
 """
 from . import neural_network
 from .condition import (Condition, ConditionExtra, Symbols, UnsupportedDerivative, grad, unpack)
-from .generation import Generator
+from .generation import DeviceGenerator, Generator, ResidualAdaptiveGenerator
 from .geometry import Hypercube
 from .jet import jet_order
 from .neural_network import FFNN, FNN, FourierFeatureNetwork, ResNet, XavierFNN
@@ -18,7 +18,7 @@ from .regularization import (AdaptiveConditionsAndPointsLosses, AdaptiveConditio
 from .trainer import Trainer, TrainerMultiGPU, TrainerOneBatch
 
 __version__ = "0.1.0"
-__all__ = ["neural_network", "Condition", "ConditionExtra", "Symbols", "grad", "unpack", "Generator",
+__all__ = ["neural_network", "Condition", "ConditionExtra", "Symbols", "grad", "unpack", "Generator", "DeviceGenerator", "ResidualAdaptiveGenerator",
            "Hypercube", "jet_order", "FNN", "XavierFNN", "ResNet", "FourierFeatureNetwork", "FFNN",
            "PINN", "ConstantLosses", "GradientLosses", "NormalLosses", "PointwiseLosses", "AdaptiveConditionsLosses",
            "AdaptiveConditionsAndPointsLosses", "install", "uninstall", "Trainer", "TrainerOneBatch", "TrainerMultiGPU", "UnsupportedDerivative"]

@@ -473,3 +473,36 @@ def test_inference_wrapper(oracle_backend):
     inf.launch_points = 40         # several launches stack to the same answer
     with torch.no_grad():
         assert torch.equal(inf(pts), y)
+
+
+def test_device_generators(oracle_backend):
+    """DeviceGenerator: uniform points inside the box, reproducible with a seed.  ResidualAdaptiveGenerator: the
+    error field comes from the value-only residual program and the added points favour large residuals."""
+    g = load("poisson_2D_1C")
+    model, conds, pinn = build_pinn("poisson_2D_1C", g)
+    c = conds[0]
+    gen = mp.DeviceGenerator(500, seed=3)
+    a = gen.generate(c, model)
+    assert a.shape == (500, 2) and a.requires_grad and a.dtype == torch.float32
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 0.5
+    b = mp.DeviceGenerator(500, seed=3).generate(c, model)
+    assert torch.equal(a, b) and not torch.equal(a, gen.generate(c, model))
+    rar = mp.ResidualAdaptiveGenerator(64, density_rec_points_num=400, add_points=40, n_points_up_bnd=150, seed=1)
+    rar.use_for(c)
+    c.points = None
+    c.update_points(model)
+    assert c.points.shape == (64, 2)
+    oracle_backend.calls.clear()
+    c.update_points(model)
+    assert c.points.shape == (104, 2)
+    kinds = [k[0] for k in oracle_backend.calls]
+    assert kinds.count("fwd") == 1 and kinds.count("resid") == 1 and "bwd" not in kinds   # value-only error field
+    pool = rar._uniform(400, c.geometry, torch.device("cpu"))
+    err = rar.error_field(c, model, pool)
+    eager = torch.stack([r.detach() for r in c.get_residual_fn(model)(pool.clone().requires_grad_())], 1).abs().sum(1)
+    assert relerr(err.numpy(), eager.numpy()) < 1e-5
+    c.update_points(model)
+    c.update_points(model)
+    assert c.points.shape[0] == 184
+    c.update_points(model)                 # upper bound reached: unchanged
+    assert c.points.shape[0] == 184

@@ -122,7 +122,9 @@ class CudaBackend:
         forward / reverse launch)."""
         st = prog.struct()
         nb = len(jets)
-        offs = [jet_offset * b.o * 4 for b in prog.blocks]
+        if isinstance(jet_offset, int):
+            jet_offset = [jet_offset] * nb
+        offs = [o * b.o * 4 for o, b in zip(jet_offset, prog.blocks)]
         jp = (ctypes.c_void_p * nb)(*[t.data_ptr() + o for t, o in zip(jets, offs)]) if nb else None
         dp = None
         if djets is not None:

@@ -43,6 +43,11 @@ class ConditionRunner:
             bb.points_prog = prog.points_program(b)
             bb.x = bb.out = bb.dout = bb.stash = None
             self.blocks.append(bb)
+        # several model calls of the same jet order (model(arg) and model(arg + 1), a periodic boundary ...) are
+        # STACKED: one forward and one reverse launch over the concatenated points of all calls, the residual
+        # program reads call b at point offset b * n of the shared jet block
+        keys = {(bb.order, tuple(bb.lap) if bb.lap is not None else None) for bb in self.blocks}
+        self.stacked = len(self.blocks) > 1 and len(keys) == 1
 
     # -- batching: conditions whose single model call has the same jet order share ONE forward and ONE reverse
     #    launch over their concatenated points (fewer tail waves and launches); each keeps its own residual program,
@@ -69,6 +74,18 @@ class ConditionRunner:
             return False
         eng = self.engine
         self.n = n
+        if self.stacked:
+            B, bb0 = len(self.blocks), self.blocks[0]
+            self.xcat = torch.empty((B * n, eng.d), dtype=torch.float32, device=device)
+            self.out_cat = torch.empty((eng.n_jets(bb0.order), B * n, eng.n_out), dtype=torch.float32, device=device)
+            self.dout_cat = torch.empty_like(self.out_cat)
+            self.stash_cat = torch.empty(eng.stash_floats(bb0.order, B * n), dtype=torch.float32, device=device)
+            ident = [b for b, bb in enumerate(self.blocks) if bb.points_prog is None]
+            for b, bb in enumerate(self.blocks):
+                bb.x = self.xcat[b * n:(b + 1) * n]
+            # the condition's own points are copied straight into the slice of the call that uses them unchanged
+            self.x = self.blocks[ident[0]].x if ident else torch.empty((n, eng.d), dtype=torch.float32, device=device)
+            return True
         self.x = torch.empty((n, eng.d), dtype=torch.float32, device=device)
         for bb in self.blocks:
             bb.x = self.x if bb.points_prog is None else torch.empty_like(self.x)
@@ -86,6 +103,16 @@ class ConditionRunner:
 
     def launch(self, weights, sums, dflat):
         eng = self.engine
+        if self.stacked:
+            be, bb0, n, B = backend(), self.blocks[0], self.n, len(self.blocks)
+            for bb in self.blocks:
+                if bb.points_prog is not None:
+                    be.residual_program(bb.points_prog, self.x, [], None, None, None, bb.x, point_major=True)
+            eng.forward(self.xcat, bb0.order, True, lap=bb0.lap, out=self.out_cat, stash=self.stash_cat)
+            be.residual_program(self.prog, self.x, [self.out_cat] * B, [self.dout_cat] * B, weights, sums,
+                                jet_offset=[b * n for b in range(B)], jet_stride=B * n)
+            eng.backward_into(self.xcat, bb0.order, self.dout_cat, self.stash_cat, dflat, lap=bb0.lap)
+            return
         self._forward_blocks(self.x, self.blocks, True)
         backend().residual_program(self.prog, self.x, [bb.out for bb in self.blocks],
                                    [bb.dout for bb in self.blocks], weights, sums)

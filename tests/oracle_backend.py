@@ -58,10 +58,11 @@ class OracleBackend:
         self.calls.append(("resid", int(x.shape[0])))
         prog.struct()   # exercises the limits / ctypes packing the CUDA backend relies on
         n = int(x.shape[0])
-        if jet_stride:     # batched conditions: this launch works on a slice of longer jet blocks
-            jets = [j[:, jet_offset:jet_offset + n] for j in jets]
+        if jet_stride:     # batched conditions / stacked blocks: this launch works on slices of longer jet blocks
+            offs = [jet_offset] * len(jets) if isinstance(jet_offset, int) else list(jet_offset)
+            jets = [j[:, o:o + n] for j, o in zip(jets, offs)]
             if djets is not None:
-                djets = [None if t is None else t[:, jet_offset:jet_offset + n] for t in djets]
+                djets = [None if t is None else t[:, o:o + n] for t, o in zip(djets, offs)]
         vals, sm, dj = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
                                    self._np(x), [self._np(j) for j in jets],
                                    None if weights is None else self._np(weights), want_seeds=djets is not None)

@@ -344,3 +344,25 @@ def test_regularizer_policies_run_on_the_fused_step(kind, oracle_backend):
         if kind != "constant":
             assert relerr(flam, elam) < 1e-5
     assert np.abs(fw - ew).max() < 1e-6
+
+
+def test_model_calls_of_one_residual_are_stacked_into_one_launch(oracle_backend):
+    """regression_1D (u(x) * u(x + 1) - x) and burgers' periodic boundary call the model twice: one forward and one
+    reverse launch over the 2n stacked points, the shifted points produced on the device."""
+    for name, ci in (("regression_1D", 0), ("burgers_1D", 1)):
+        g = load(name)
+        model, conds, pinn = build_pinn(name, g)
+        tr = mp.TrainerOneBatch(pinn, torch.optim.SGD(model.parameters(), lr=0.0), None, num_epochs=1,
+                                update_grid_every=10**9)
+        fs = tr.fused_step()
+        assert fs.runners[ci].stacked
+        n = len(g[f"pts{ci}"])
+        oracle_backend.calls.clear()
+        pinn.select_batch(0)
+        tr._train_batches()
+        fwd = [c for c in oracle_backend.calls if c[0] == "fwd"]
+        assert (fwd[ci][2] if name == "regression_1D" else sorted(c[2] for c in fwd)[-1]) == 2 * n or \
+            any(c[2] == 2 * n for c in fwd)
+        assert sum(1 for c in oracle_backend.calls if c[0] == "bwd") == len(fs.units)
+        assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_f64"]) < 1e-5
+        assert relerr(model.jet_engine.flat_grad.numpy(), g["grad_f64"]) < 1e-5

@@ -146,15 +146,28 @@ def test_residual_kernel_matches_oracle_interpreter(name, cuda_backend):
         w = torch.rand(K, device="cuda") + 0.5
         sums = torch.zeros(K, device="cuda")
         vals = torch.empty((K, n), device="cuda")
-        r._forward_blocks(r.x, r.blocks, True)
-        cuda_backend.residual_program(prog, r.x, [b.out for b in r.blocks], [b.dout for b in r.blocks], w, sums, vals)
-        jets = [b.out.cpu().numpy().astype(np.float64) for b in r.blocks]
+        if r.stacked:     # several model calls: one forward over the stacked points, the program reads slices
+            B = len(r.blocks)
+            for b in r.blocks:
+                if b.points_prog is not None:
+                    cuda_backend.residual_program(b.points_prog, r.x, [], None, None, None, b.x, point_major=True)
+            model.jet_engine.forward(r.xcat, r.blocks[0].order, True, lap=r.blocks[0].lap, out=r.out_cat,
+                                     stash=r.stash_cat)
+            cuda_backend.residual_program(prog, r.x, [r.out_cat] * B, [r.dout_cat] * B, w, sums, vals,
+                                          jet_offset=[i * n for i in range(B)], jet_stride=B * n)
+            outs = [r.out_cat[:, i * n:(i + 1) * n] for i in range(B)]
+            douts = [r.dout_cat[:, i * n:(i + 1) * n] for i in range(B)]
+        else:
+            r._forward_blocks(r.x, r.blocks, True)
+            cuda_backend.residual_program(prog, r.x, [b.out for b in r.blocks], [b.dout for b in r.blocks], w, sums, vals)
+            outs, douts = [b.out for b in r.blocks], [b.dout for b in r.blocks]
+        jets = [o.cpu().numpy().astype(np.float64) for o in outs]
         rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
                                  x.cpu().numpy().astype(np.float64), jets, w.cpu().numpy().astype(np.float64))
         assert relerr(vals.cpu().numpy(), rv) < 2e-6
         assert relerr(sums.cpu().numpy(), rs) < 2e-6
-        for b, ref in zip(r.blocks, rd):
-            assert relerr(b.dout.cpu().numpy(), ref) < 2e-6
+        for dj, ref in zip(douts, rd):
+            assert relerr(dj.cpu().numpy(), ref) < 2e-6
         for kk in range(K):
             assert relerr(vals[kk].cpu().numpy(), g[f"res{ci}_{k}_f64"]) < TOL, (ci, k)
             k += 1

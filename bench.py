@@ -538,6 +538,15 @@ def run_ours(args):
                         og = ours0[1].double()
                         par[f"loss_rel_err_vs_{dt_name}"] = abs(ours0[0] - float(rt)) / abs(float(rt))
                         par[f"grad_rel_err_vs_{dt_name}"] = float((og - rg).abs().max() / rg.abs().max())
+                        # the same, normalised inside every parameter tensor (the global maximum sits in the last
+                        # layer and would hide the earlier ones): worst tensor
+                        worst = 0.0
+                        for p_, off_ in zip(model.jet_engine._params, model.jet_engine._offsets):
+                            sl_ = slice(off_, off_ + p_.numel())
+                            den_ = float(rg[sl_].abs().max())
+                            if p_.requires_grad and den_ > 0:
+                                worst = max(worst, float((og[sl_] - rg[sl_]).abs().max()) / den_)
+                        par[f"grad_rel_err_worst_tensor_vs_{dt_name}"] = worst
                         del rm, rpts, rt, rg
                     except Exception as ex:
                         par[f"{dt_name}_unavailable"] = str(ex)[:120]

@@ -45,15 +45,28 @@ constexpr float kGeluC = 1.0f / 1.41421f;             // the reference's literal
 constexpr float kGeluC2 = kGeluC * kGeluC;
 constexpr float kInvSqrtPi = 0.5641895835477563f;
 
+// -DMPINN_ACCURATE_GELU=1 (diagnostic builds, scripts/build_variant.sh) swaps the two hardware approximations of the
+// GELU basis for the accurate library functions, to measure what they cost in accuracy
+#ifndef MPINN_ACCURATE_GELU
+#define MPINN_ACCURATE_GELU 0
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
+#if MPINN_ACCURATE_GELU
+  return exp2f(x);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float rcp_approx(float x) {
+#if MPINN_ACCURATE_GELU
+  return 1.0f / x;
+#else
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // Phi(z) = 0.5 (1 + erf(c z)) and c/sqrt(pi) exp(-(c z)^2) from ONE exponential, branch-free:

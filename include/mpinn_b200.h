@@ -37,6 +37,10 @@ enum { MPINN_ACT_NONE = 0, MPINN_ACT_SINE = 1, MPINN_ACT_GELU = 2 };
 enum { MPINN_FLAG_SAVE_SKIP = 1, MPINN_FLAG_ADD_SKIP = 2 };
 enum { MPINN_ENGINE_AUTO = 0, MPINN_ENGINE_FFMA = 1, MPINN_ENGINE_TCGEN05 = 2 };
 #define MPINN_ORDER_LAPLACE 3
+#define MPINN_ORDER_HESSIAN 4   /* value, d first, d diagonal second, then the d(d-1)/2 mixed second derivatives
+                                   (pairs i<j in the order (0,1), (0,2), (1,2)): J = 1 + 2d + d(d-1)/2.  What
+                                   grad(u_x, arg) returns in its off-diagonal columns in the reference
+                                   (condition/diff.py:47).  FP32-FMA engine only. */
 
 /* One layer of the network "program" (host struct, passed by pointer to host memory).
  *   LINEAR : z = W h + b (+ skip), a = act(z); W is [out_dim,in_dim] at params+w_off, b at params+b_off

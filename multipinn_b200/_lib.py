@@ -21,6 +21,7 @@ ACT_NONE, ACT_SINE, ACT_GELU = 0, 1, 2
 FLAG_SAVE_SKIP, FLAG_ADD_SKIP = 1, 2
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05 = 0, 1, 2
 ORDER_LAPLACE = 3
+ORDER_HESSIAN = 4
 
 # every symbol include/mpinn_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {

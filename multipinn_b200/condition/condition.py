@@ -129,13 +129,20 @@ class Condition:
         derivatives the jet path provides."""
         probe = self._probe_point(model)
         residuals = self.get_residual_fn(model)(probe)
+        if any(isinstance(r, torch.Tensor) and bool(torch.isnan(r).any()) for r in residuals) and probe.shape[1] >= 2:
+            # a NaN-poisoned mixed second derivative is used: raise every second-order model call of this residual to
+            # the full-Hessian mode and evaluate again
+            plan = self.plan_for(model)
+            if plan is not None and any(o == 2 for o in plan.orders):
+                plan.orders = [4 if o == 2 else o for o in plan.orders]
+                residuals = self.get_residual_fn(model)(probe)
         self.output_len = len(residuals)
         for k, r in enumerate(residuals):
             if isinstance(r, torch.Tensor) and bool(torch.isnan(r).any()):
                 raise UnsupportedDerivative(
                     f"residual component {k} of {getattr(self.function, '__name__', self.function)} is NaN at "
-                    "the probe point: it most likely uses a mixed second derivative, which the fused jet "
-                    "path does not compute (only d2/dx_i^2).")
+                    "the probe point (also with the full-Hessian jets): it uses a derivative the fused jet path "
+                    "does not compute, or the residual itself is not finite there.")
         self._trace(model, probe)
 
 

@@ -46,7 +46,8 @@ static const char* build_prog(const mpinn_op_t* ops, int n_ops, int d, int order
   if (!ops || n_ops <= 0) return "empty program";
   if (n_ops > kMaxOps) return "program has more than MPINN_MAX_OPS ops";
   if (d < 1 || d > 3) return "input dimension must be 1, 2 or 3";
-  if (order < 0 || order > 3) return "jet order must be 0, 1, 2 or 3 (MPINN_ORDER_LAPLACE)";
+  if (order < 0 || order > 4) return "jet order must be 0, 1, 2, 3 (MPINN_ORDER_LAPLACE) or 4 (MPINN_ORDER_HESSIAN)";
+  if (order == 4 && d < 2) return "MPINN_ORDER_HESSIAN needs at least two input dimensions (use order 2)";
   DevProg& p = *out;
   memset(&p, 0, sizeof(p));
   p.n_ops = n_ops;

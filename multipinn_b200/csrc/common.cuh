@@ -35,7 +35,14 @@ struct DevProg {
 };
 
 // number of jet channels: order 0/1/2 -> 1 + order*d;  order 3 (MPINN_ORDER_LAPLACE) -> value, d first derivatives, L
-__host__ __device__ constexpr int jet_count(int d, int order) { return order == 3 ? d + 2 : 1 + order * d; }
+// order 4 (MPINN_ORDER_HESSIAN) -> value, d first, d diagonal second and d(d-1)/2 mixed second derivatives, the
+// mixed pairs (i < j) in the order (0,1), (0,2), (1,2) after the diagonal ones
+__host__ __device__ constexpr int jet_count(int d, int order) {
+  return order == 3 ? d + 2 : (order == 4 ? 1 + 2 * d + d * (d - 1) / 2 : 1 + order * d);
+}
+// first / second direction of mixed pair m for dimension D
+__host__ __device__ constexpr int mixed_i(int D, int m) { return (D == 3 && m == 2) ? 1 : 0; }
+__host__ __device__ constexpr int mixed_j(int D, int m) { return (D == 3 && m >= 1) ? 2 : 1; }
 
 // internal activation code: cos z, i.e. the second half of a Fourier encoding [sin(xB), cos(xB)] seen as a
 // LINEAR(x -> xB) layer followed by an activation (reference neural_network/fourier_features.py:37-40)
@@ -158,7 +165,12 @@ __device__ __forceinline__ void act_jets(int act, float* z, const float* lc) {
     for (int i = 0; i < D; ++i) q = fmaf(lc[i] * z[1 + i], z[1 + i], q);
     z[1 + D] = fmaf(s2, q, s1 * z[1 + D]);
   }
-  if (ORDER == 2) {
+  if (ORDER == 4) {
+#pragma unroll
+    for (int m = 0; m < D * (D - 1) / 2; ++m)
+      z[1 + 2 * D + m] = fmaf(s2 * z[1 + mixed_i(D, m)], z[1 + mixed_j(D, m)], s1 * z[1 + 2 * D + m]);
+  }
+  if (ORDER == 2 || ORDER == 4) {
 #pragma unroll
     for (int i = 0; i < D; ++i) z[1 + D + i] = fmaf(s2 * z[1 + i], z[1 + i], s1 * z[1 + D + i]);
   }
@@ -182,12 +194,20 @@ __device__ __forceinline__ void sincos_jets(const float* z, float* sj, float* cj
       cj[1 + i] = -s * z[1 + i];
     }
   }
-  if (ORDER == 2) {
+  if (ORDER == 2 || ORDER == 4) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const float zi2 = z[1 + i] * z[1 + i];
       sj[1 + D + i] = fmaf(-s, zi2, c * z[1 + D + i]);
       cj[1 + D + i] = fmaf(-c, zi2, -s * z[1 + D + i]);
+    }
+  }
+  if (ORDER == 4) {
+#pragma unroll
+    for (int m = 0; m < D * (D - 1) / 2; ++m) {
+      const float zz = z[1 + mixed_i(D, m)] * z[1 + mixed_j(D, m)];
+      sj[1 + 2 * D + m] = fmaf(-s, zz, c * z[1 + 2 * D + m]);
+      cj[1 + 2 * D + m] = fmaf(-c, zz, -s * z[1 + 2 * D + m]);
     }
   }
   if (ORDER == 3) {
@@ -222,13 +242,27 @@ __device__ __forceinline__ void act_jets_bwd(int act, const float* z, float* ab,
     ab[0] = zb0;
     return;
   }
+  float mixb[D > 0 ? D : 1];   // contributions of the mixed channels to the first-derivative channels
+#pragma unroll
+  for (int i = 0; i < D; ++i) mixb[i] = 0.0f;
+  if (ORDER == 4) {
+#pragma unroll
+    for (int m = 0; m < D * (D - 1) / 2; ++m) {
+      const int i = mixed_i(D, m), j = mixed_j(D, m);
+      const float aij = ab[1 + 2 * D + m], zi = z[1 + i], zj = z[1 + j];
+      mixb[i] = fmaf(aij * s2, zj, mixb[i]);
+      mixb[j] = fmaf(aij * s2, zi, mixb[j]);
+      zb0 = fmaf(aij, fmaf(s3 * zi, zj, s2 * z[1 + 2 * D + m]), zb0);
+      ab[1 + 2 * D + m] = aij * s1;
+    }
+  }
   if (ORDER >= 1) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const float zi = z[1 + i];
-      float zbi = ab[1 + i] * s1;
+      float zbi = fmaf(ab[1 + i], s1, mixb[i]);
       zb0 = fmaf(ab[1 + i] * s2, zi, zb0);
-      if (ORDER == 2) {
+      if (ORDER == 2 || ORDER == 4) {
         const float aii = ab[1 + D + i];
         zbi = fmaf(2.0f * aii * s2, zi, zbi);
         zb0 = fmaf(aii, fmaf(s3 * zi, zi, s2 * z[1 + D + i]), zb0);

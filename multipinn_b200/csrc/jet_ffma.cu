@@ -81,9 +81,13 @@ __device__ __forceinline__ void fourier_jets(float* buf, int W, const float* __r
       const float b = __ldg(B + i * m + f);
       z[0] = fmaf(xv[i], b, z[0]);
       if (ORDER >= 1) z[1 + i] = b;
-      if (ORDER == 2) z[1 + D + i] = 0.0f;
+      if (ORDER == 2 || ORDER == 4) z[1 + D + i] = 0.0f;
     }
     if (ORDER == 3) z[1 + D] = 0.0f;
+    if (ORDER == 4) {
+#pragma unroll
+      for (int m = 0; m < D * (D - 1) / 2; ++m) z[1 + 2 * D + m] = 0.0f;
+    }
     sincos_jets<D, ORDER>(z, sj, cj, lc);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -449,6 +453,8 @@ cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(1, 3, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(2, 3, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 3, 32, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(2, 4, 32, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(3, 4, 32, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 0, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 1, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(1, 2, 16, launch_fwd_t) FWD_ARGS;
@@ -461,6 +467,8 @@ cudaError_t launch_fwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(1, 3, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(2, 3, 16, launch_fwd_t) FWD_ARGS;
   MPINN_DISPATCH(3, 3, 16, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(2, 4, 16, launch_fwd_t) FWD_ARGS;
+  MPINN_DISPATCH(3, 4, 16, launch_fwd_t) FWD_ARGS;
 #undef FWD_ARGS
   return cudaErrorInvalidValue;
 }
@@ -487,6 +495,8 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(1, 3, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(2, 3, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 3, 32, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(2, 4, 32, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(3, 4, 32, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 0, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 1, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(1, 2, 16, launch_bwd_t) BWD_ARGS;
@@ -499,6 +509,8 @@ cudaError_t launch_bwd_ffma(const DevProg& prog, const float* params, const floa
   MPINN_DISPATCH(1, 3, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(2, 3, 16, launch_bwd_t) BWD_ARGS;
   MPINN_DISPATCH(3, 3, 16, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(2, 4, 16, launch_bwd_t) BWD_ARGS;
+  MPINN_DISPATCH(3, 4, 16, launch_bwd_t) BWD_ARGS;
 #undef BWD_ARGS
   return cudaErrorInvalidValue;
 }

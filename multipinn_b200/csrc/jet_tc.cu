@@ -548,6 +548,7 @@ jet_fwd_tc(const __grid_constant__ DevProg prog, const float* __restrict__ param
 // host side
 // ---------------------------------------------------------------------------------------------
 bool tc_forward_supported(const DevProg& prog, int d, int order) {
+  if (order > 3) return false;   // mixed second derivatives run on the FP32-FMA engine
   const int J = jet_count(d, order);
   if (prog.has_skip && prog.ops[0].kind == MPINN_OP_FOURIER) return false;   // no combined kernel variant
   if (J * kTcW > 448) return false;

@@ -294,7 +294,11 @@ class JetEngine:
         self.generation += 1
 
     def n_jets(self, order: int) -> int:
-        return self.d + 2 if order == _lib.ORDER_LAPLACE else 1 + order * self.d
+        if order == _lib.ORDER_LAPLACE:
+            return self.d + 2
+        if order == _lib.ORDER_HESSIAN:
+            return 1 + 2 * self.d + self.d * (self.d - 1) // 2
+        return 1 + order * self.d
 
     def tc_supported(self, order: int) -> bool:
         """Whether the tcgen05 engine runs this program at ``order`` (cached host-side query)."""

@@ -15,9 +15,13 @@ How many derivative orders a call needs is discovered by running the residual fu
 and remembered per (condition, model-call index) in a ``ResidualPlan``.  A call that turns out to
 need more than planned is transparently re-run at the higher order.
 
-Not supported (raises, never silently wrong): mixed second derivatives that are actually *used*
-(they come back NaN-poisoned and the probe rejects NaN residuals), derivatives of order >= 3,
-``grad`` of anything that is not a direct view of a model output.
+Mixed second derivatives: a block of order <= 2 carries only the diagonal ones, and the off-diagonal columns of
+``grad(u_x, arg)`` come back NaN-poisoned.  When the probe finds a NaN residual (i.e. a mixed derivative is
+actually *used*) the condition's plan is raised to the full-Hessian mode (order 4: d(d-1)/2 extra channels,
+FP32-FMA engine) and those columns become real.
+
+Not supported (raises, never silently wrong): derivatives of order >= 3, ``grad`` of anything that is not a direct
+view of a model output.
 """
 from __future__ import annotations
 
@@ -261,6 +265,8 @@ def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
     if j > d:
         raise UnsupportedDerivative("third and higher derivatives are not supported by the jet path")
     need = 1 if j == 0 else 2
+    if b.order == 3:
+        raise UnsupportedDerivative("internal: Laplace-mode blocks are only produced for traced residuals")
     if b.order < need:
         # the plan under-estimated this call: run it again at the needed order and remember
         if b.plan is not None and b.plan_idx >= 0:
@@ -280,9 +286,14 @@ def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
     if j == 0:
         return out[1:1 + d, :, k].t()
     i = j - 1
-    cols = [_nan_column(b.n, out)] * d
-    cols = list(cols)
-    cols[i] = out[1 + d + i, :, k]
+    if b.order == 4:      # full-Hessian block: the off-diagonal columns are real
+        pairs = [(a, c) for a in range(d) for c in range(a + 1, d)]
+        cols = [out[1 + d + i, :, k] if c == i else out[1 + 2 * d + pairs.index((min(i, c), max(i, c))), :, k]
+                for c in range(d)]
+    else:
+        cols = [_nan_column(b.n, out)] * d
+        cols = list(cols)
+        cols[i] = out[1 + d + i, :, k]
     res = torch.stack(cols, dim=1)
     res._jet_block = out  # keep the block (and its registry entry) alive as long as the result is
     return res

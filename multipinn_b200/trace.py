@@ -34,6 +34,7 @@ OP_POWI, OP_POWF = 30, 31
 
 MAX_INSTR, MAX_CONST, MAX_OUT, MAX_BLOCKS, MAX_JO = 192, 64, 8, 4, 32
 ORDER_LAPLACE = 3
+ORDER_HESSIAN = 4        # diagonal AND mixed second derivatives: channels 2d+1.. are the pairs (0,1), (0,2), (1,2)
 ENABLE_LAPLACE = True    # module switch for A/B measurements (bench.py --no-laplace); the rewrite is exact
 
 _BINARY = {OP_ADD, OP_SUB, OP_MUL, OP_DIV}
@@ -45,7 +46,17 @@ class TraceError(Exception):
 
 
 def n_jets(d: int, order: int) -> int:
-    return d + 2 if order == ORDER_LAPLACE else 1 + order * d
+    if order == ORDER_LAPLACE:
+        return d + 2
+    if order == ORDER_HESSIAN:
+        return 1 + 2 * d + d * (d - 1) // 2
+    return 1 + order * d
+
+
+def mixed_index(d: int, i: int, j: int) -> int:
+    """Channel (full numbering) of d2/dx_i dx_j, i != j."""
+    pairs = [(a, c) for a in range(d) for c in range(a + 1, d)]
+    return 1 + 2 * d + pairs.index((min(i, j), max(i, j)))
 
 
 class RInstr(ctypes.Structure):
@@ -547,9 +558,12 @@ def traced_grad(u, arg) -> TMat:
         return TMat(tr, [tr.leaf(("j", b, 1 + i, k)) for i in range(d)], "grad", b)
     if j <= d:
         blk.order = max(blk.order, 2)
+        if d == 1:
+            return TMat(tr, [tr.leaf(("j", b, 2, k))], "grad", b)
         i0 = j - 1
-        cols = [tr.leaf(("j", b, 1 + d + i0, k)) if i == i0 else
-                _Poison("mixed second derivatives are not computed by the fused jet path (only d2/dx_i^2)")
+        # off-diagonal columns are mixed second derivatives: real leaves; a block whose live program reads one runs
+        # in the full-Hessian mode (order 4), otherwise they are dead code
+        cols = [tr.leaf(("j", b, 1 + d + i0, k)) if i == i0 else tr.leaf(("j", b, mixed_index(d, i0, i), k))
                 for i in range(d)]
         return TMat(tr, cols, "grad", b)
     raise UnsupportedDerivative("third and higher derivatives are not supported by the jet path")
@@ -584,6 +598,7 @@ def trace_residual(function, model, d: int, like: torch.Tensor) -> ResidualProgr
     prog = ResidualProgram(d, tr.instrs, tr.consts, outs, tr.blocks)
     for b in range(len(tr.blocks)):
         prog.points_program(b)      # raises if a block's points depend on a model output
+    prog = eliminate_dead(prog)        # (requested-but-unused mixed derivatives must not block the Laplace mode)
     prog = laplace_rewrite(prog)
     prog = simplify(prog)
     prog = eliminate_dead(prog)
@@ -688,14 +703,14 @@ def renumber_jets(prog: ResidualProgram) -> ResidualProgram:
     used = [0] * len(prog.blocks)
     for op, a, b, c in prog.instrs:
         if op == OP_LOADJ:
-            lvl = 0 if b == 0 else (1 if b <= d else 2)
+            lvl = 0 if b == 0 else (1 if b <= d else (2 if b <= 2 * d else ORDER_HESSIAN))
+            if prog.blocks[a].order == ORDER_LAPLACE and lvl == 2:
+                lvl = ORDER_LAPLACE
             used[a] = max(used[a], lvl)
     for b, blk in enumerate(prog.blocks):
-        if blk.order == ORDER_LAPLACE:
-            if used[b] < 2:
-                blk.order, blk.lap = used[b], None
-        else:
-            blk.order = used[b]
+        blk.order = used[b]
+        if blk.order != ORDER_LAPLACE:
+            blk.lap = None
     instrs = []
     for op, a, b, c in prog.instrs:
         if op == OP_LOADJ:
@@ -734,6 +749,8 @@ def laplace_rewrite(prog: ResidualProgram) -> ResidualProgram:
     for i, (op, a, b, c) in enumerate(prog.instrs):
         if op == OP_CONST:
             cval[i] = prog.consts[a]
+        elif op == OP_LOADJ and b > 2 * d:
+            bad[a] = True                         # a live mixed second derivative: full-Hessian mode, no Laplace channel
         elif op == OP_LOADJ and b > d:
             lin[i] = {(a, c, b - 1 - d): 1.0}    # (block, output k, direction)
         elif op in (OP_ADD, OP_SUB):

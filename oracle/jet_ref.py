@@ -54,10 +54,21 @@ GELU_C = 1.0 / 1.41421  # the reference divides by the literal 1.41421, not sqrt
 
 
 ORDER_LAPLACE = 3
+ORDER_HESSIAN = 4   # value, d first derivatives, d diagonal second derivatives, d(d-1)/2 mixed ones: pairs (i<j) in
+                    # the order (0,1), (0,2), (1,2) -- what `grad(u_x, arg)` returns in ALL its columns in the reference
+                    # (condition/diff.py:47), used e.g. by examples/surfaces_elliptic/problem.py:15-25
+
+
+def mixed_pairs(d: int):
+    return [(i, j) for i in range(d) for j in range(i + 1, d)]
 
 
 def n_jets(d: int, order: int) -> int:
-    return d + 2 if order == ORDER_LAPLACE else 1 + order * d
+    if order == ORDER_LAPLACE:
+        return d + 2
+    if order == ORDER_HESSIAN:
+        return 1 + 2 * d + d * (d - 1) // 2
+    return 1 + order * d
 
 
 def _lap(lap, d, dtype):
@@ -104,9 +115,12 @@ def _act_jets(act, z, d, order, lap=None):
     if order >= 1:
         for i in range(d):
             a[:, 1 + i] = ders[1] * z[:, 1 + i]
-    if order == 2:
+    if order in (2, ORDER_HESSIAN):
         for i in range(d):
             a[:, 1 + d + i] = ders[2] * z[:, 1 + i] ** 2 + ders[1] * z[:, 1 + d + i]
+    if order == ORDER_HESSIAN:
+        for m, (i, j) in enumerate(mixed_pairs(d)):
+            a[:, 1 + 2 * d + m] = ders[2] * z[:, 1 + i] * z[:, 1 + j] + ders[1] * z[:, 1 + 2 * d + m]
     return a
 
 
@@ -132,7 +146,14 @@ def _act_jets_bwd(act, z, abar, d, order, lap=None):
             zi = z[:, 1 + i]
             zb[:, 1 + i] = abar[:, 1 + i] * ders[1]
             zb[:, 0] += abar[:, 1 + i] * ders[2] * zi
-    if order == 2:
+    if order == ORDER_HESSIAN:
+        for m, (i, j) in enumerate(mixed_pairs(d)):
+            zi, zj, zij, aij = z[:, 1 + i], z[:, 1 + j], z[:, 1 + 2 * d + m], abar[:, 1 + 2 * d + m]
+            zb[:, 1 + 2 * d + m] = aij * ders[1]
+            zb[:, 1 + i] += aij * ders[2] * zj
+            zb[:, 1 + j] += aij * ders[2] * zi
+            zb[:, 0] += aij * (ders[3] * zi * zj + ders[2] * zij)
+    if order in (2, ORDER_HESSIAN):
         for i in range(d):
             zi = z[:, 1 + i]
             zii = z[:, 1 + d + i]
@@ -162,9 +183,12 @@ def _cos_jets(z, d, order, lap=None):
     if order >= 1:
         for i in range(d):
             c[:, 1 + i] = -sz * z[:, 1 + i]
-    if order == 2:
+    if order in (2, ORDER_HESSIAN):
         for i in range(d):
             c[:, 1 + d + i] = -cz * z[:, 1 + i] ** 2 - sz * z[:, 1 + d + i]
+    if order == ORDER_HESSIAN:
+        for m, (i, j) in enumerate(mixed_pairs(d)):
+            c[:, 1 + 2 * d + m] = -cz * z[:, 1 + i] * z[:, 1 + j] - sz * z[:, 1 + 2 * d + m]
     if order == ORDER_LAPLACE:
         w = _lap(lap, d, z.dtype)
         q = sum(w[i] * z[:, 1 + i] ** 2 for i in range(d))
@@ -230,7 +254,14 @@ def backward(program, params: np.ndarray, x: np.ndarray, order: int, cache, dout
                     zi = z[:, 1 + i]
                     zb[:, 1 + i] += cbar[:, 1 + i] * (-sz)
                     zb[:, 0] += cbar[:, 1 + i] * (-cz) * zi
-            if order == 2:
+            if order == ORDER_HESSIAN:
+                for q, (i, j) in enumerate(mixed_pairs(d)):
+                    zi, zj, zij, cij = z[:, 1 + i], z[:, 1 + j], z[:, 1 + 2 * d + q], cbar[:, 1 + 2 * d + q]
+                    zb[:, 1 + 2 * d + q] += cij * (-sz)
+                    zb[:, 1 + i] += cij * (-cz) * zj
+                    zb[:, 1 + j] += cij * (-cz) * zi
+                    zb[:, 0] += cij * (sz * zi * zj - cz * zij)
+            if order in (2, ORDER_HESSIAN):
                 for i in range(d):
                     zi, zii = z[:, 1 + i], z[:, 1 + d + i]
                     cii = cbar[:, 1 + d + i]

@@ -416,3 +416,80 @@ def test_points_grad_matches_reference_backward_on_cuda(name):
     for c, x in zip(conds, pts):
         assert c.points.grad is not None
         assert relerr(c.points.grad.cpu().numpy(), x.grad.numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------ full-Hessian jets (mixed partials)
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D", "navier_stokes_3D", "burgers_1D"])
+def test_full_hessian_jets_match_oracle(name, cuda_backend):
+    """order 4: value, first, diagonal AND mixed second derivatives (FP32-FMA engine) against the fp64 oracle,
+    forward and reverse; the first 1 + 2d channels equal the order-2 jets; an explicit tcgen05 request is refused."""
+    g = load(name)
+    m = golden_model(name, g)
+    x_np = g["pts0"]
+    n, d = x_np.shape
+    x = torch.tensor(x_np).cuda()
+    e = m.jet_engine
+    out4, stash = e.forward(x, 4, need_stash=True)
+    J = 1 + 2 * d + d * (d - 1) // 2
+    assert out4.shape[0] == J
+    prog, flat = AR.build_program(m)
+    ref, cache = JR.forward(prog, flat, x_np.astype(np.float64), 4)
+    assert relerr(out4.cpu().numpy().transpose(1, 0, 2), ref) < TOL
+    out2, _ = e.forward(x, 2, need_stash=False)
+    assert relerr(out4[:1 + 2 * d].cpu().numpy(), out2.cpu().numpy()) < TOL
+    rng = np.random.default_rng(4)
+    dout_np = rng.standard_normal((n, J, int(g["output_dim"]))).astype(np.float32)
+    dout = torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda()
+    dflat = e.backward(x, 4, dout, stash).cpu().numpy()
+    ref_dp, _ = JR.backward(prog, flat, x_np.astype(np.float64), 4, cache, dout_np.astype(np.float64))
+    if prog[0, 0] == JR.OP_FOURIER:
+        ref_dp[prog[0, 3]: prog[0, 3] + prog[0, 1] * prog[0, 2] // 2] = 0
+    assert relerr(dflat, ref_dp) < TOL
+    assert not cuda_backend.engine_supports(m.jet_program(), d, 4, _lib.ENGINE_TCGEN05)
+
+
+def test_mixed_partial_residual_trains_on_the_fused_step():
+    """A residual that uses u_xy: traced into an order-4 program, fused CUDA-graph step vs the eager jet path and vs
+    nested autograd of the reference algorithm in fp64."""
+    torch.manual_seed(3)
+
+    def make(ns):
+        def fn(m, a):
+            (u,) = ns.unpack(m(a))
+            x, y = ns.unpack(a)
+            u_x, u_y = ns.unpack(ns.grad(u, a))
+            u_xx, u_xy = ns.unpack(ns.grad(u_x, a))
+            _, u_yy = ns.unpack(ns.grad(u_y, a))
+            return [u_xx * u_yy - u_xy**2 - torch.exp(x) * y, u_x + u_xy]
+        return fn
+
+    pts = torch.rand((3000, 2), generator=torch.Generator().manual_seed(0))
+    trainers = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        model = mp.FNN(2, 1, [64, 64, 64]).cuda()
+        cond = mp.Condition(make(types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack)), mp.Hypercube([0, 0], [1, 1]))
+        p = pts.cuda().requires_grad_()
+        cond.generator = types.SimpleNamespace(n_points=3000, generate=lambda c, m, p=p: p)
+        pinn = mp.PINN(model, [cond])
+        pinn.update_data()
+        tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-3), None, num_epochs=4,
+                                update_grid_every=10**9)
+        tr.use_fused_step = fused
+        assert (tr.fused_step() is not None) == fused
+        assert cond.plan_for(model).orders == [4] and cond.program_for(model).blocks[0].order == 4
+        trainers.append((tr, model))
+    ref = AR.MODELS["FNN"](2, 1, hidden_layers=[64, 64, 64]).double().cuda()
+    ref.load_state_dict({k: v.double() for k, v in trainers[0][1].state_dict().items()})
+    total, losses = AR.mean_loss(ref, [make(types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack))],
+                                 [pts.double().cuda().requires_grad_()])
+    for e in range(4):
+        for tr, _ in trainers:
+            tr.current_epoch = e + 1
+            tr._train_epoch()
+        a, b = trainers[0][0], trainers[1][0]
+        if e == 0:
+            assert relerr(a.epoch_loss_detailed.cpu().numpy(), losses.detach().cpu().numpy()) < TOL
+        assert relerr(float(a.total_loss), float(b.total_loss)) < 2e-5
+    d = (trainers[0][1].jet_engine.flat.detach() - trainers[1][1].jet_engine.flat.detach()).abs().max()
+    assert float(d) < 2e-5

@@ -167,9 +167,23 @@ def test_unsupported_derivatives_raise(oracle_backend):
         u_xx, u_xy = mp.unpack(mp.grad(u_x, arg))
         return [u_xy]
 
+    # a mixed derivative that is USED raises the condition to the full-Hessian jets (order 4) at the probe
     c = mp.Condition(mixed, mp.Hypercube([0, 0], [1, 1]))
-    with pytest.raises(mp.UnsupportedDerivative):
-        c.init_output_len(model)
+    c.init_output_len(model)
+    assert c.plan_for(model).orders == [4]
+    (r,) = c.get_residual_fn(model)(pts)
+    assert relerr(r.detach().numpy(), _uxy_fp64(model, g["pts0"])) < 1e-5
+
+
+def _uxy_fp64(model, pts_np):
+    """d2u/dxdy by nested autograd of the reference algorithm (oracle port) in fp64."""
+    ref = AR.MODELS["FNN"](2, 1, **GOLD_KW["poisson_2D_1C"]).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    x = torch.tensor(pts_np, dtype=torch.float64).requires_grad_()
+    (u,) = AR.unpack(ref(x))
+    u_x, _ = AR.unpack(AR.grad(u, x))
+    _, u_xy = AR.unpack(AR.grad(u_x, x))
+    return u_xy.detach().numpy()
 
 
 def test_symbols_generated_source():

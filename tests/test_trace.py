@@ -253,7 +253,7 @@ def test_untraceable_residuals_fall_back_to_eager(oracle_backend):
     assert np.isfinite(float(tr.total_loss))
 
 
-def test_mixed_derivative_is_rejected_when_used_and_harmless_when_not():
+def test_mixed_derivative_selects_full_hessian_mode_only_when_used():
     model = _small_model()
 
     def unused(m, a):
@@ -266,11 +266,62 @@ def test_mixed_derivative_is_rejected_when_used_and_harmless_when_not():
         (u,) = mp.unpack(m(a))
         u_x, u_y = mp.unpack(mp.grad(u, a))
         u_xx, u_xy = mp.unpack(mp.grad(u_x, a))
-        return [u_xy + u]
+        u_yx, u_yy = mp.unpack(mp.grad(u_y, a))
+        return [u_xy * u_yx + u_xx + u_yy + u]
 
-    assert _trace(unused, model).blocks[0].order == 3
-    with pytest.raises(mp.UnsupportedDerivative):
-        _trace(used, model)
+    assert _trace(unused, model).blocks[0].order == 3      # requested but dead: still one Laplace channel
+    p = _trace(used, model)
+    assert p.blocks[0].order == 4                          # value, 2 first, 2 diagonal, 1 mixed
+    loads = sorted(ins[2] for ins in p.instrs if ins[0] == trace.OP_LOADJ)
+    assert loads == [0, 3, 4, 5]                           # u, u_xx, u_yy, u_xy (u_yx is the same channel)
+    # values against the eager residual (which now escalates its plan to order 4 instead of raising)
+    rng = np.random.default_rng(2)
+    x = rng.random((17, 2))
+    vals, _, _ = _eval(p, model, x)
+    c = mp.Condition(used, mp.Hypercube([0, 0], [1, 1]))
+    c.init_output_len(model)
+    assert c.plan_for(model).orders == [4] and c.program_for(model) is not None
+    eager = c.get_residual_fn(model)(torch.tensor(x, dtype=torch.float32).requires_grad_())
+    assert relerr(vals[0], eager[0].detach().numpy().astype(np.float64)) < 1e-6
+
+
+def test_full_hessian_fused_step_matches_autograd(oracle_backend):
+    """A residual with a mixed derivative through the fused step (order-4 jets, FP32-FMA engine on the device):
+    loss and parameter gradient against nested torch autograd of the reference algorithm (oracle port, fp64)."""
+    from oracle import autograd_ref as AR
+    torch.manual_seed(1)
+    model = mp.FNN(2, 1, [16, 16])
+
+    def make(ns):
+        def fn(m, a):
+            (u,) = ns.unpack(m(a))
+            x, y = ns.unpack(a)
+            u_x, u_y = ns.unpack(ns.grad(u, a))
+            u_xx, u_xy = ns.unpack(ns.grad(u_x, a))
+            _, u_yy = ns.unpack(ns.grad(u_y, a))
+            return [u_xx * u_yy - u_xy**2 - torch.exp(x) * y, u_x + u_xy]   # Monge-Ampere-like + a linear use
+        return fn
+
+    cond = mp.Condition(make(types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack)), mp.Hypercube([0, 0], [1, 1]))
+    pts = torch.rand((40, 2), generator=torch.Generator().manual_seed(0)).requires_grad_()
+    cond.generator = types.SimpleNamespace(n_points=40, generate=lambda c, m: pts)
+    pinn = mp.PINN(model, [cond])
+    pinn.update_data()
+    tr = mp.TrainerOneBatch(pinn, torch.optim.SGD(model.parameters(), lr=0.0), None, num_epochs=1,
+                            update_grid_every=10**9)
+    assert tr.fused_step() is not None and cond.program_for(model).blocks[0].order == 4
+    pinn.select_batch(0)
+    tr._train_batches()
+    ref = AR.MODELS["FNN"](2, 1, hidden_layers=[16, 16]).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    rfn = make(types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack))
+    total, losses = AR.mean_loss(ref, [rfn], [pts.detach().double().requires_grad_()])
+    total.backward()
+    rgrad = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                            for p in ref.parameters()])
+    assert relerr(tr.epoch_loss_detailed.numpy(), losses.detach().numpy()) < 1e-5
+    assert relerr(float(tr.total_loss), float(total)) < 1e-5
+    assert relerr(model.jet_engine.flat_grad.numpy(), rgrad) < 1e-5
 
 
 def test_program_struct_roundtrip_and_limits():

@@ -34,7 +34,7 @@ extern "C" {
 
 enum { MPINN_OP_LINEAR = 0, MPINN_OP_FOURIER = 1 };
 enum { MPINN_ACT_NONE = 0, MPINN_ACT_SINE = 1, MPINN_ACT_GELU = 2 };
-enum { MPINN_FLAG_SAVE_SKIP = 1, MPINN_FLAG_ADD_SKIP = 2 };
+enum { MPINN_FLAG_SAVE_SKIP = 1, MPINN_FLAG_ADD_SKIP = 2, MPINN_FLAG_TRAINABLE = 4 };
 enum { MPINN_ENGINE_AUTO = 0, MPINN_ENGINE_FFMA = 1, MPINN_ENGINE_TCGEN05 = 2 };
 #define MPINN_ORDER_LAPLACE 3
 #define MPINN_ORDER_HESSIAN 4   /* value, d first, d diagonal second, then the d(d-1)/2 mixed second derivatives
@@ -48,7 +48,8 @@ enum { MPINN_ENGINE_AUTO = 0, MPINN_ENGINE_FFMA = 1, MPINN_ENGINE_TCGEN05 = 2 };
  *   FOURIER: a = [sin(xB), cos(xB)], B is [in_dim,out_dim/2] at params+w_off
  *            (reference neural_network/fourier_features.py:30-40)
  *   flags  : SAVE_SKIP remembers this op's input; ADD_SKIP adds it before the activation
- *            (reference neural_network/light_residual_block.py:33-38)                       */
+ *            (reference neural_network/light_residual_block.py:33-38); TRAINABLE on a FOURIER op asks the reverse
+ *            pass for dL/dB (FourierEncoding(is_trainable=True), fourier_features.py:30-32; FP32-FMA engine)   */
 typedef struct mpinn_op {
   int32_t kind, in_dim, out_dim, w_off, b_off, act, flags, reserved;
 } mpinn_op_t;

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("MPINN_B200_LIB") or os.path.join(_HERE, "csrc", "libm
 ABI_VERSION = 2
 OP_LINEAR, OP_FOURIER = 0, 1
 ACT_NONE, ACT_SINE, ACT_GELU = 0, 1, 2
-FLAG_SAVE_SKIP, FLAG_ADD_SKIP = 1, 2
+FLAG_SAVE_SKIP, FLAG_ADD_SKIP, FLAG_TRAINABLE = 1, 2, 4
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05 = 0, 1, 2
 ORDER_LAPLACE = 3
 ORDER_HESSIAN = 4

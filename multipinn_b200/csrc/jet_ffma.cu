@@ -237,7 +237,42 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
 
     for (int l = prog.n_ops - 1; l >= 0; --l) {
       const DevOp& op = prog.ops[l];
-      if (op.kind == MPINN_OP_FOURIER) break;  // frozen encoding: nothing upstream needs a gradient
+      if (op.kind == MPINN_OP_FOURIER) {
+        // A frozen encoding needs nothing upstream.  A trainable one (reference fourier_features.py:30-32): bufG holds
+        // abar for [sin(xB) | cos(xB)]; both halves flow back into z = xB, and dL/dB[i][f] = sum over points of
+        // zbar_0[f] x_i + zbar_{1+i}[f]  (z's first-derivative channel i is B[i][f] itself, the second-order ones 0).
+        if (!(op.flags & MPINN_FLAG_TRAINABLE)) break;
+        const int m = op.out_dim / 2;
+        const float* B = params + op.w_off;
+        for (int f = g; f < m; f += G) {
+          float z[J], as[J], ac[J];
+          z[0] = 0.0f;
+#pragma unroll
+          for (int j = 1; j < J; ++j) z[j] = 0.0f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const float b = __ldg(B + i * m + f);
+            z[0] = fmaf(xv[i], b, z[0]);
+            if (ORDER >= 1) z[1 + i] = b;
+          }
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            as[j] = bufG[(j * W + f) * TPP + p];
+            ac[j] = bufG[(j * W + m + f) * TPP + p];
+          }
+          act_jets_bwd<D, ORDER>(MPINN_ACT_SINE, z, as, prog.lap_c);
+          act_jets_bwd<D, ORDER>(kActCos, z, ac, prog.lap_c);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              float gb = (as[0] + ac[0]) * xv[i];
+              if (ORDER >= 1) gb += as[1 + i] + ac[1 + i];
+              atomicAdd(part + op.w_off + i * m + f, gb);
+            }
+          }
+        }
+        break;
+      }
 
       // (1) z-bar = act'(z) applied to a-bar, in place; keep a copy for the skip branch
       if (op.act != MPINN_ACT_NONE || (op.flags & MPINN_FLAG_ADD_SKIP)) {
@@ -279,7 +314,8 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
           }
         }
       }
-      const bool need_dinput = (l > 0) && !(prog.ops[l - 1].kind == MPINN_OP_FOURIER);
+      const bool need_dinput = (l > 0) && !(prog.ops[l - 1].kind == MPINN_OP_FOURIER &&
+                                            !(prog.ops[l - 1].flags & MPINN_FLAG_TRAINABLE));
       if (need_dinput) copy_to_smem(Ws, packed + op.pk_bwd, op.out_dim * op.inp);
       __syncthreads();
 

@@ -214,7 +214,7 @@ class JetEngine:
         self._params = []
         self._offsets = []
         self._tc_ok = {}
-        self.has_skip = bool((self.ops[:, 6] != 0).any())
+        self.has_skip = bool(((self.ops[:, 6] & (_lib.FLAG_SAVE_SKIP | _lib.FLAG_ADD_SKIP)) != 0).any())
 
     # ---------------------------------------------------------------- flat buffers
     def _is_flat(self) -> bool:

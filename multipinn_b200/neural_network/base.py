@@ -38,7 +38,8 @@ class ProgramBuilder:
                           self.offsets[id(lin.weight)], self.offsets[id(lin.bias)], act, flags, 0])
 
     def fourier(self, B: torch.Tensor):
-        self.rows.append([_lib.OP_FOURIER, B.shape[0], 2 * B.shape[1], self.offsets[id(B)], 0, 0, 0, 0])
+        flags = _lib.FLAG_TRAINABLE if B.requires_grad else 0   # a trainable encoding runs on the FP32-FMA engine
+        self.rows.append([_lib.OP_FOURIER, B.shape[0], 2 * B.shape[1], self.offsets[id(B)], 0, 0, flags, 0])
 
     def array(self) -> np.ndarray:
         return np.asarray(self.rows, dtype=np.int32)

@@ -1,6 +1,7 @@
 """Fourier-feature network (reference ``multipinn/neural_network/fourier_features.py:9-76``):
-``gamma(x) = [sin(xB), cos(xB)]`` with a frozen ``B ~ N(0, sigma^2)`` followed by an ``FNN``.
-The encoding jets are evaluated in registers inside the fused kernel (``x@B`` once, not twice)."""
+``gamma(x) = [sin(xB), cos(xB)]`` with ``B ~ N(0, sigma^2)`` followed by an ``FNN``.
+The encoding jets are evaluated in registers inside the fused kernel (``x@B`` once, not twice).  A frozen ``B`` (the
+default) runs on the tcgen05 engine; ``is_trainable=True`` adds ``dL/dB`` to the reverse pass of the FP32-FMA engine."""
 from typing import List, Literal
 
 import torch
@@ -41,9 +42,6 @@ class FourierFeatureNetwork(JetModule):
             self.fnn = FNN(encoding_dim, output_dim, hidden_layers)
 
     def jet_program(self):
-        if self.fourier_encoding.B.requires_grad:
-            raise NotImplementedError(
-                "FourierFeatureNetwork(is_trainable=True): the fused reverse pass treats B as frozen")
         b = ProgramBuilder(self)
         b.fourier(self.fourier_encoding.B)
         fnn_rows(b, self.fnn.network_layers)

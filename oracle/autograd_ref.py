@@ -185,7 +185,7 @@ def build_program(model):
         fnn_ops(model)
     elif name in ("FourierFeatureNetwork",):
         B = model.fourier_encoding.B
-        ops.append([J.OP_FOURIER, B.shape[0], 2 * B.shape[1], offs[id(B)], 0, 0, 0, 0])
+        ops.append([J.OP_FOURIER, B.shape[0], 2 * B.shape[1], offs[id(B)], 0, 0, 4 if B.requires_grad else 0, 0])
         fnn_ops(model.fnn)
     elif name == "ResNet":
         mods = list(model.layers)

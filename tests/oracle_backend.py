@@ -49,7 +49,7 @@ class OracleBackend:
             dx.copy_(torch.from_numpy(np.ascontiguousarray(dxx)).to(dx.dtype))
         # frozen Fourier encodings get no gradient from the fused reverse pass
         ops = np.asarray(ops).reshape(-1, 8)
-        if ops[0, 0] == JR.OP_FOURIER:
+        if ops[0, 0] == JR.OP_FOURIER and not (ops[0, 6] & 4):
             dp[ops[0, 3]: ops[0, 3] + ops[0, 1] * ops[0, 2] // 2] = 0
         dparams.add_(torch.from_numpy(dp).to(dparams.dtype))
 

@@ -493,3 +493,29 @@ def test_mixed_partial_residual_trains_on_the_fused_step():
         assert relerr(float(a.total_loss), float(b.total_loss)) < 2e-5
     d = (trainers[0][1].jet_engine.flat.detach() - trainers[1][1].jet_engine.flat.detach()).abs().max()
     assert float(d) < 2e-5
+
+
+@pytest.mark.parametrize("order,lap", [(0, None), (1, None), (2, None), (3, (1.0, 0.5, 2.0)), (4, None)])
+def test_trainable_fourier_matrix_gradient_matches_oracle(order, lap, cuda_backend):
+    """FourierFeatureNetwork(is_trainable=True): dL/dB from the FP32-FMA reverse pass vs the fp64 oracle, every jet
+    order; the tcgen05 engine declines the program (it treats B as frozen)."""
+    torch.manual_seed(7)
+    m = mp.FFNN(3, 4, hidden_layers=[64, 64, 64], encoding_dim=64, sigma=1.0, is_trainable=True).cuda()
+    assert not cuda_backend.engine_supports(m.jet_program(), 3, 2, _lib.ENGINE_TCGEN05)
+    n = 777
+    rng = np.random.default_rng(order)
+    x_np = rng.random((n, 3), dtype=np.float32)
+    x = torch.tensor(x_np).cuda()
+    e = m.jet_engine
+    out, stash = e.forward(x, order, need_stash=True, lap=lap)
+    dout_np = rng.standard_normal((n, out.shape[0], 4)).astype(np.float32)
+    dflat = e.backward(x, order, torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda(), stash,
+                       lap=lap).cpu().numpy()
+    prog, flat = AR.build_program(m)
+    assert prog[0, 6] == 4
+    ref, cache = JR.forward(prog, flat, x_np.astype(np.float64), order, lap)
+    ref_dp, _ = JR.backward(prog, flat, x_np.astype(np.float64), order, cache, dout_np.astype(np.float64), lap)
+    nB = 3 * 32
+    assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref) < TOL
+    assert relerr(dflat, ref_dp) < TOL
+    assert relerr(dflat[:nB], ref_dp[:nB]) < TOL and np.abs(ref_dp[:nB]).max() > 0

@@ -520,3 +520,45 @@ def test_device_generators(oracle_backend):
     assert c.points.shape[0] == 184
     c.update_points(model)                 # upper bound reached: unchanged
     assert c.points.shape[0] == 184
+
+
+def test_trainable_fourier_matrix_gets_a_gradient(oracle_backend):
+    """FourierFeatureNetwork(is_trainable=True) (reference fourier_features.py:30-32): the program marks the encoding
+    trainable, the reverse pass returns dL/dB, and loss / gradient equal nested autograd of the reference algorithm."""
+    torch.manual_seed(4)
+    model = mp.FFNN(3, 2, hidden_layers=[16, 16], encoding_dim=16, sigma=1.0, is_trainable=True)
+    prog = model.jet_program()
+    assert prog[0, 0] == 1 and prog[0, 6] == 4
+    assert np.array_equal(prog, AR.build_program(model)[0])
+
+    def make(ns):
+        def fn(m, a):
+            u, v = ns.unpack(m(a))
+            u_x, u_y, u_z = ns.unpack(ns.grad(u, a))
+            u_xx, _, _ = ns.unpack(ns.grad(u_x, a))
+            _, v_y, _ = ns.unpack(ns.grad(v, a))
+            return [u_xx + v_y * u - u_z, v - u_y]
+        return fn
+
+    cond = mp.Condition(make(types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack)), mp.Hypercube([0, 0, 0], [1, 1, 1]))
+    pts = torch.rand((50, 3), generator=torch.Generator().manual_seed(0)).requires_grad_()
+    cond.generator = types.SimpleNamespace(n_points=50, generate=lambda c, m: pts)
+    pinn = mp.PINN(model, [cond])
+    pinn.update_data()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=1, update_grid_every=10**9)
+    assert tr._flat_adam is not None
+    ref = AR.MODELS["FFNN"](3, 2, hidden_layers=[16, 16], encoding_dim=16, sigma=1.0, is_trainable=True).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    total, losses = AR.mean_loss(ref, [make(types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack))],
+                                 [pts.detach().double().requires_grad_()])
+    total.backward()
+    rgrad = np.concatenate([p.grad.numpy().reshape(-1) for p in ref.parameters()])
+    B0 = model.fourier_encoding.B.detach().clone()
+    pinn.select_batch(0)
+    tr.current_epoch = 1
+    tr._train_epoch()
+    assert relerr(tr.epoch_loss_detailed.numpy(), losses.detach().numpy()) < 1e-5
+    assert relerr(model.jet_engine.flat_grad.numpy(), rgrad) < 1e-5
+    assert float(model.jet_engine.flat_grad[:B0.numel()].abs().max()) > 0
+    assert not torch.equal(model.fourier_encoding.B.detach(), B0)          # B is trained

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPINN_ABI_VERSION 2
+#define MPINN_ABI_VERSION 3
 #define MPINN_MAX_OPS 64
 
 enum { MPINN_OP_LINEAR = 0, MPINN_OP_FOURIER = 1 };
@@ -134,6 +134,8 @@ int mpinn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * straight-line SSA program over per-point scalars: instruction i defines register i.
  *   CONST a        r = consts[a]                       LOADX a      r = x[n][a]
  *   LOADJ a b      r = jets[a][j][n][k], b = j*o + k   (block a = the a-th model(arg) call)
+ *   LOADD a        r = data[n][a]                      (per-point auxiliary data of ConditionExtra, e.g. boundary
+ *                                                       normals: reference condition/condition.py:117-215)
  *   ADD SUB MUL DIV a b ;  NEG SIN COS EXP TANH RELU ABS SQRT LOG a ;  POWI a b (integer exponent b) ;
  *   POWF a b (exponent = constant register b)
  * jet_reg[a][j*o+k] is the register that loads that channel, or -1 if the residual does not read it. */
@@ -147,7 +149,8 @@ enum {
 #define MPINN_RP_MAX_INSTR 192
 #define MPINN_RP_MAX_CONST 64
 #define MPINN_RP_MAX_OUT 8
-#define MPINN_RP_MAX_BLOCKS 4
+#define MPINN_RP_MAX_BLOCKS 8
+#define MPINN_RP_MAX_DATA 16
 #define MPINN_RP_MAX_JO 32
 
 typedef struct mpinn_rinstr { int16_t op, a, b, c; } mpinn_rinstr_t;
@@ -166,6 +169,7 @@ typedef struct mpinn_rprog {
  *                 autograd graph between the residual list and the network outputs)
  *   values[k][n] = r_k[n]                                       (optional: what Condition.get_residual returns;
  *                                                                 values_point_major != 0 stores values[n][k] instead)
+ * data is the device [n, n_data] row-major block LOADD reads (NULL when prog->n_data == 0).
  * prog_host and the two pointer tables are HOST memory; jets[a] / djets[a] are device [J_a, n, o_a] blocks.
  * djets, weights (device [n_out]), sums (device [n_out]) and values may each be NULL.  jet_stride (0 = n) is the
  * number of points of the jet blocks when they are longer than this launch's n: several conditions of the same
@@ -174,7 +178,7 @@ typedef struct mpinn_rprog {
  * calls (n_blocks == 0, jets_host NULL) is allowed: it maps point columns to point columns, which is how the points
  * of a second model call such as model(arg + 1) (reference examples/regression_1D/problem.py:17-35) or a shifted
  * boundary (examples/burgers_1D/problem.py:20-25) are produced on the device. */
-int mpinn_residual_program(const mpinn_rprog_t* prog_host, const float* x, int64_t n,
+int mpinn_residual_program(const mpinn_rprog_t* prog_host, const float* x, const float* data, int64_t n,
                            const float* const* jets_host, float* const* djets_host,
                            const float* weights, float* sums, float* values, int values_point_major,
                            int64_t jet_stride, void* stream);

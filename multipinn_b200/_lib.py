@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MPINN_B200_LIB selects a diagnostic build of the same library (scripts/build_variant.sh); it is never a fallback
 LIB_PATH = os.environ.get("MPINN_B200_LIB") or os.path.join(_HERE, "csrc", "libmpinn_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OP_LINEAR, OP_FOURIER = 0, 1
 ACT_NONE, ACT_SINE, ACT_GELU = 0, 1, 2
 FLAG_SAVE_SKIP, FLAG_ADD_SKIP, FLAG_TRAINABLE = 1, 2, 4
@@ -37,8 +37,8 @@ SIGNATURES = {
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_size_t, c_int, c_void_p]),
     "mpinn_engine_supports": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
-    "mpinn_residual_program": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_int, c_int64, c_void_p]),
+    "mpinn_residual_program": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "mpinn_adam_tick": (c_int, [c_void_p, c_float, c_float, c_void_p]),
     "mpinn_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float,
                                     c_float, c_float, c_float, c_void_p]),

@@ -55,14 +55,15 @@ class Condition:
         points of the bounding box.  Any failure leaves the condition on the eager jet path."""
         from ..neural_network.base import JetModule
         self.trace_note = None
-        if not isinstance(model, JetModule) or type(self).get_residual is not Condition.get_residual:
+        if not isinstance(model, JetModule) or \
+                type(self).get_residual not in (Condition.get_residual, ConditionExtra.get_residual):
             return
         try:
             self._programs[model] = None
         except TypeError:
             return
         try:
-            prog = _trace.trace_residual(self.function, model, model.jet_engine.d, probe)
+            prog = _trace.trace_residual(self.function, model, model.jet_engine.d, probe, self._trace_data(probe))
             self._check_program(model, prog, probe)
         except (_trace.TraceError, UnsupportedDerivative) as e:
             self.trace_note = f"{type(e).__name__}: {e}"
@@ -72,13 +73,20 @@ class Condition:
             return
         self._programs[model] = prog
 
-    def _check_program(self, model, prog, probe: torch.Tensor, n: int = 8) -> None:
-        from ..fused import ConditionRunner
+    def _trace_data(self, probe: torch.Tensor):
+        """Sample of the per-point data the residual takes besides the points (None for a plain Condition)."""
+        return None
+
+    def _check_points(self, probe: torch.Tensor, n: int) -> torch.Tensor:
         low = torch.as_tensor(self.geometry.bbox[0], dtype=torch.float32, device=probe.device)
         high = torch.as_tensor(self.geometry.bbox[1], dtype=torch.float32, device=probe.device)
         gen = torch.Generator(device="cpu").manual_seed(1234)
         u = torch.rand((n, low.numel()), generator=gen, dtype=torch.float32).to(probe.device)
-        x = (low + (high - low) * u).contiguous()
+        return (low + (high - low) * u).contiguous()
+
+    def _check_program(self, model, prog, probe: torch.Tensor, n: int = 8) -> None:
+        from ..fused import ConditionRunner
+        x = self._check_points(probe, n)
         with torch.no_grad():
             got = ConditionRunner(self, prog, model.jet_engine).residual_values(x)
         want = self.get_residual_fn(model)(x.clone().requires_grad_())
@@ -182,3 +190,24 @@ class ConditionExtra(Condition):
             return self._call(model, arg, self.data_gen(arg))
 
         return residual
+
+    def _trace_data(self, probe: torch.Tensor):
+        return self.data_gen(probe)
+
+    def _check_points(self, probe: torch.Tensor, n: int) -> torch.Tensor:
+        # data generators such as boundary normals are only meaningful ON the geometry: check there when it can
+        # be sampled (fixed seed; the caller's numpy random stream is left as it was)
+        try:
+            import numpy as np
+            state = np.random.get_state()
+            np.random.seed(1234)
+            try:
+                pts = self.geometry.random_points(n, "pseudo")
+            finally:
+                np.random.set_state(state)
+            x = torch.as_tensor(np.asarray(pts), dtype=torch.float32, device=probe.device).contiguous()
+            if x.dim() == 2 and x.shape[0] >= 1 and x.shape[1] == probe.shape[1] and bool(torch.isfinite(x).all()):
+                return x
+        except Exception:   # noqa: BLE001 -- geometry without a sampler: fall back to the bounding box
+            pass
+        return super()._check_points(probe, n)

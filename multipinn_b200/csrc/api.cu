@@ -32,7 +32,8 @@ cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* pack
 cudaError_t read_tc_debug(long long* out, int n);
 cudaError_t read_tc_debug_fwd(long long* out, int n);
 // residual.cu
-cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
+cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, const float* data, int64_t n,
+                            const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
                             int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream);
 cudaError_t launch_adam_tick(float* state, float beta1, float beta2, cudaStream_t stream);
@@ -348,8 +349,8 @@ int mpinn_engine_supports(const mpinn_op_t* ops, int n_ops, int d, int order, in
   return 1;   // the FP32-FMA engine runs every valid program (shared-memory budget is checked at launch)
 }
 
-int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n, const float* const* jets,
-                           float* const* djets, const float* weights, float* sums, float* values,
+int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, const float* data, int64_t n,
+                           const float* const* jets, float* const* djets, const float* weights, float* sums, float* values,
                            int values_point_major, int64_t jet_stride, void* stream) {
   if (!prog || !x) return fail("null pointer");
   if (prog->n_blocks > 0 && !jets) return fail("residual program: null jet table");
@@ -361,6 +362,8 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n,
   if (prog->n_blocks < 0 || prog->n_blocks > MPINN_RP_MAX_BLOCKS) return fail("residual program: bad block count");
   if (prog->n_const < 0 || prog->n_const > MPINN_RP_MAX_CONST) return fail("residual program: bad constant count");
   if (prog->d < 1 || prog->d > 3) return fail("residual program: bad input dimension");
+  if (prog->n_data < 0 || prog->n_data > MPINN_RP_MAX_DATA) return fail("residual program: bad data column count");
+  if (prog->n_data > 0 && !data) return fail("residual program: null data block");
   for (int b = 0; b < prog->n_blocks; ++b) {
     if (!jets[b]) return fail("residual program: null jet block");
     if (prog->block_o[b] < 1 || prog->block_J[b] < 1 || prog->block_J[b] * prog->block_o[b] > MPINN_RP_MAX_JO)
@@ -373,6 +376,7 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n,
     switch (in.op) {
       case MPINN_RP_CONST: ok = in.a >= 0 && in.a < prog->n_const; break;
       case MPINN_RP_LOADX: ok = in.a >= 0 && in.a < prog->d; break;
+      case MPINN_RP_LOADD: ok = in.a >= 0 && in.a < prog->n_data; break;
       case MPINN_RP_LOADJ:
         ok = in.a >= 0 && in.a < prog->n_blocks && in.b >= 0 && in.b < prog->block_J[in.a] * prog->block_o[in.a];
         break;
@@ -390,7 +394,7 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, int64_t n,
   DeviceInfo info;
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
-  e = launch_residual(*prog, x, n, jets, djets, weights, sums, values, values_point_major, jet_stride,
+  e = launch_residual(*prog, x, data, n, jets, djets, weights, sums, values, values_point_major, jet_stride,
                       info.sm_count, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("residual_program", e);
   return 0;

@@ -38,7 +38,7 @@ __device__ __forceinline__ float powi(float v, int k) {
 template <bool SEEDS>
 __global__ void __launch_bounds__(kResidThreads)
 residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, const float* __restrict__ x,
-                int64_t n, const float* __restrict__ weights, float* __restrict__ sums,
+                const float* __restrict__ data, int64_t n, const float* __restrict__ weights, float* __restrict__ sums,
                 float* __restrict__ values, int values_point_major, int64_t jstride) {
   extern __shared__ float rp_smem[];
   const int t = threadIdx.x;
@@ -60,6 +60,7 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
       switch (in.op) {
         case MPINN_RP_CONST: r = prog.consts[in.a]; break;
         case MPINN_RP_LOADX: r = __ldg(x + pt * prog.d + in.a); break;
+        case MPINN_RP_LOADD: r = __ldg(data + pt * prog.n_data + in.a); break;
         case MPINN_RP_LOADJ: {
           const int o = prog.block_o[in.a];
           const int j = in.b / o, k = in.b - j * o;
@@ -164,7 +165,8 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
   }
 }
 
-cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n, const float* const* jets,
+cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, const float* data, int64_t n,
+                            const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
                             int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream) {
   const int64_t jstride = jet_stride > 0 ? jet_stride : n;
@@ -182,13 +184,13 @@ cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, int64_t n
   if (seeds) {
     e = cudaFuncSetAttribute(residual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    residual_kernel<true><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, n, weights, sums, values,
-                                                                             values_point_major, jstride);
+    residual_kernel<true><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, data, n, weights, sums,
+                                                                             values, values_point_major, jstride);
   } else {
     e = cudaFuncSetAttribute(residual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    residual_kernel<false><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, n, weights, sums, values,
-                                                                              values_point_major, jstride);
+    residual_kernel<false><<<(unsigned)blocks, kResidThreads, smem, stream>>>(prog, io, x, data, n, weights, sums,
+                                                                              values, values_point_major, jstride);
   }
   return cudaGetLastError();
 }

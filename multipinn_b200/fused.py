@@ -35,6 +35,8 @@ class ConditionRunner:
         self.K = len(prog.outputs)
         self.n = -1
         self.x = None
+        self.data = None            # [n, n_data] per-point data block of a ConditionExtra (LOADD)
+        self._data_src = None
         self.blocks: List[_BlockBuffers] = []
         for b, blk in enumerate(prog.blocks):
             bb = _BlockBuffers()
@@ -62,11 +64,26 @@ class ConditionRunner:
         self.group, self.n0 = group, n0
         self.n = group.counts[group.members.index(self)]
         self.x = group.x[n0:n0 + self.n]
+        self._bind_data(self.n, group.x.device)
+
+    def _bind_data(self, n: int, device):
+        w = self.prog.data_width
+        self.data = torch.empty((n, w), dtype=torch.float32, device=device) if w else None
+        self._data_src = None
+
+    def load_batch(self):
+        """Copy the condition's current batch (points and, for a ConditionExtra, its data) into the static buffers."""
+        c = self.cond
+        self.x.copy_(c.batch_points.detach(), non_blocking=True)
+        if self.data is not None and c.batch_data is not self._data_src:   # data change only with the points set
+            from .trace import pack_data
+            pack_data(c.batch_data, self.n, out=self.data)
+            self._data_src = c.batch_data
 
     def launch_residual_shared(self, weights, sums):
         g = self.group
         backend().residual_program(self.prog, self.x, [g.out], [g.dout], weights, sums,
-                                   jet_offset=self.n0, jet_stride=g.n_total)
+                                   jet_offset=self.n0, jet_stride=g.n_total, data=self.data)
 
     def bind(self, n: int, device) -> bool:
         """(Re)allocate the static buffers for n points; True if they changed (a captured graph is then stale)."""
@@ -74,6 +91,7 @@ class ConditionRunner:
             return False
         eng = self.engine
         self.n = n
+        self._bind_data(n, device)
         if self.stacked:
             B, bb0 = len(self.blocks), self.blocks[0]
             self.xcat = torch.empty((B * n, eng.d), dtype=torch.float32, device=device)
@@ -94,11 +112,11 @@ class ConditionRunner:
             bb.stash = torch.empty(eng.stash_floats(bb.order, n), dtype=torch.float32, device=device)
         return True
 
-    def _forward_blocks(self, x, blocks, need_stash):
+    def _forward_blocks(self, x, blocks, need_stash, data=None):
         eng, be = self.engine, backend()
         for bb in blocks:
             if bb.points_prog is not None:   # e.g. model(arg + 1): the shifted points are produced on the device
-                be.residual_program(bb.points_prog, x, [], None, None, None, bb.x, point_major=True)
+                be.residual_program(bb.points_prog, x, [], None, None, None, bb.x, point_major=True, data=data)
             eng.forward(bb.x, bb.order, need_stash, lap=bb.lap, out=bb.out, stash=bb.stash)
 
     def launch(self, weights, sums, dflat):
@@ -107,23 +125,28 @@ class ConditionRunner:
             be, bb0, n, B = backend(), self.blocks[0], self.n, len(self.blocks)
             for bb in self.blocks:
                 if bb.points_prog is not None:
-                    be.residual_program(bb.points_prog, self.x, [], None, None, None, bb.x, point_major=True)
+                    be.residual_program(bb.points_prog, self.x, [], None, None, None, bb.x, point_major=True,
+                                        data=self.data)
             eng.forward(self.xcat, bb0.order, True, lap=bb0.lap, out=self.out_cat, stash=self.stash_cat)
             be.residual_program(self.prog, self.x, [self.out_cat] * B, [self.dout_cat] * B, weights, sums,
-                                jet_offset=[b * n for b in range(B)], jet_stride=B * n)
+                                jet_offset=[b * n for b in range(B)], jet_stride=B * n, data=self.data)
             eng.backward_into(self.xcat, bb0.order, self.dout_cat, self.stash_cat, dflat, lap=bb0.lap)
             return
-        self._forward_blocks(self.x, self.blocks, True)
+        self._forward_blocks(self.x, self.blocks, True, self.data)
         backend().residual_program(self.prog, self.x, [bb.out for bb in self.blocks],
-                                   [bb.dout for bb in self.blocks], weights, sums)
+                                   [bb.dout for bb in self.blocks], weights, sums, data=self.data)
         for bb in self.blocks:
             eng.backward_into(bb.x, bb.order, bb.dout, bb.stash, dflat, lap=bb.lap)
 
-    def residual_values(self, x: torch.Tensor) -> torch.Tensor:
+    def residual_values(self, x: torch.Tensor, data=None) -> torch.Tensor:
         """[K, N] residual components at arbitrary points, value-only (no seeds, no reverse pass): the fast path
-        for residual-driven samplers and callbacks."""
+        for residual-driven samplers and callbacks.  ``data``: the packed [N, n_data] block of a ConditionExtra
+        (default: its ``data_gen`` evaluated at ``x``)."""
         eng = self.engine
         n = x.shape[0]
+        if self.prog.data_width and data is None:
+            from .trace import pack_data
+            data = pack_data(self.cond.data_gen(x), n).to(x.device)
         tmp = []
         for bb in self.blocks:
             t = _BlockBuffers()
@@ -132,9 +155,9 @@ class ConditionRunner:
             t.out = torch.empty((eng.n_jets(bb.order), n, eng.n_out), dtype=torch.float32, device=x.device)
             t.stash = None
             tmp.append(t)
-        self._forward_blocks(x, tmp, False)
+        self._forward_blocks(x, tmp, False, data)
         vals = torch.empty((self.K, n), dtype=torch.float32, device=x.device)
-        backend().residual_program(self.prog, x, [t.out for t in tmp], None, None, None, vals)
+        backend().residual_program(self.prog, x, [t.out for t in tmp], None, None, None, vals, data=data)
         return vals
 
 
@@ -242,6 +265,10 @@ class FusedStep:
             progs.append(p)
         K = sum(len(p.outputs) for p in progs)
         if K + 1 > eng.COMM_TAIL:
+            return None
+        # a ConditionExtra hands its residual the data of ALL its points whatever the batch (reference
+        # condition/condition.py:186-188 slices the tuple, not the tensors): only consistent with one batch
+        if any(p.data_width for p in progs) and trainer.num_batches != 1:
             return None
         # the regularizers raise the reference's own exceptions for shapes they do not support: leave those to them
         if mode == "constant" and len(reg.lambdas) != K:
@@ -391,7 +418,7 @@ class FusedStep:
         conds = [r.cond for r in self.runners]
         self._bind(conds[0].batch_points.device)
         for r in self.runners:
-            r.x.copy_(r.cond.batch_points.detach(), non_blocking=True)
+            r.load_batch()
         self.engine._ensure_packed()
         self._graphed("_g_compute", self._compute)
 

@@ -109,13 +109,16 @@ class jet_order:
 
 # ----------------------------------------------------------------------------- jet blocks
 class JetBlock:
-    __slots__ = ("out_ref", "arg_ref", "arg_ptr", "n", "d", "o", "order", "engine", "plan", "plan_idx",
+    __slots__ = ("out_ref", "arg_ref", "arg_ptr", "shift_of", "n", "d", "o", "order", "engine", "plan", "plan_idx",
                  "offset0", "generation", "grad_mode", "__weakref__")
 
     def __init__(self, out, arg, order, engine, plan, plan_idx):
         self.out_ref = weakref.ref(out)
         self.arg_ref = weakref.ref(arg)
         self.arg_ptr = arg.data_ptr()
+        self.shift_of = _shift_origin(arg)
+        if self.shift_of is not None:
+            out._jet_points = arg        # a temporary (`x + c`): lives as long as the block's output does
         self.n, self.d = arg.shape
         self.o = out.shape[2]
         self.order = order
@@ -125,6 +128,30 @@ class JetBlock:
         self.offset0 = out.storage_offset()
         self.generation = engine.generation          # parameter version the block was computed with
         self.grad_mode = torch.is_grad_enabled()
+
+
+def _shift_origin(arg: torch.Tensor):
+    """``model(x + c)`` (reference examples/portal_1D_1C/problem.py:36-39 then takes ``grad(u, x)``): when the tensor
+    the model is called with is a leaf plus / minus a constant, the data pointer of that leaf -- a derivative with
+    respect to it equals the derivative with respect to the shifted points (identity Jacobian)."""
+    fn = arg.grad_fn
+    if fn is None or type(fn).__name__ not in ("AddBackward0", "SubBackward0"):
+        return None
+    nxt = fn.next_functions
+    if len(nxt) != 2:
+        return None
+    if type(fn).__name__ == "AddBackward0" and getattr(fn, "_saved_alpha", 1) != 1:
+        return None
+    (f0, _), (f1, _) = nxt
+    leaf_fn = None
+    if f0 is not None and f1 is None:
+        leaf_fn = f0
+    elif f1 is not None and f0 is None and type(fn).__name__ == "AddBackward0":
+        leaf_fn = f1
+    var = getattr(leaf_fn, "variable", None)          # AccumulateGrad
+    if var is None or tuple(var.shape) != tuple(arg.shape):
+        return None
+    return var.data_ptr()
 
 
 _blocks: Dict[int, JetBlock] = {}
@@ -258,8 +285,12 @@ def jet_grad(u: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
             "grad(u, arg): u is not a view of a model output produced by a multipinn_b200 network. "
             "Derivatives of derived expressions (e.g. grad(u*v, arg)) are not supported by the jet "
             "path; differentiate the outputs and apply the product/chain rule in the residual.")
-    if arg.data_ptr() != b.arg_ptr or tuple(arg.shape) != (b.n, b.d):
+    if tuple(arg.shape) != (b.n, b.d) or (arg.data_ptr() != b.arg_ptr and arg.data_ptr() != b.shift_of):
         raise UnsupportedDerivative("grad(u, arg): arg is not the tensor the model was called with")
+    if arg.data_ptr() != b.arg_ptr:      # model(arg + c): the block's own points
+        arg = b.arg_ref()
+        if arg is None:
+            raise UnsupportedDerivative("grad(u, arg): the shifted points the model was called with are gone")
     j, k = _decode(u, b)
     d = b.d
     if j > d:

@@ -32,7 +32,7 @@ OP_ADD, OP_SUB, OP_MUL, OP_DIV = 10, 11, 12, 13
 OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_TANH, OP_RELU, OP_ABS, OP_SQRT, OP_LOG = 20, 21, 22, 23, 24, 25, 26, 27, 28
 OP_POWI, OP_POWF = 30, 31
 
-MAX_INSTR, MAX_CONST, MAX_OUT, MAX_BLOCKS, MAX_JO = 192, 64, 8, 4, 32
+MAX_INSTR, MAX_CONST, MAX_OUT, MAX_BLOCKS, MAX_JO, MAX_DATA = 192, 64, 8, 8, 32, 16
 ORDER_LAPLACE = 3
 ORDER_HESSIAN = 4        # diagonal AND mixed second derivatives: channels 2d+1.. are the pairs (0,1), (0,2), (1,2)
 ENABLE_LAPLACE = True    # module switch for A/B measurements (bench.py --no-laplace); the rewrite is exact
@@ -95,8 +95,9 @@ class ResidualProgram:
     """Finalised program: ``instrs`` is SSA (instruction i defines register i)."""
 
     def __init__(self, d: int, instrs: List[Tuple[int, int, int, int]], consts: List[float],
-                 outputs: List[int], blocks: List[Block]):
+                 outputs: List[int], blocks: List[Block], data_width: int = 0):
         self.d = d
+        self.data_width = data_width     # columns of the per-point data block LOADD reads (ConditionExtra)
         self.instrs = instrs
         self.consts = consts
         self.outputs = outputs
@@ -114,6 +115,8 @@ class ResidualProgram:
             raise TraceError(f"residual program has {len(self.consts)} constants (limit {MAX_CONST})")
         if len(self.outputs) > MAX_OUT:
             raise TraceError(f"residual has {len(self.outputs)} components (limit {MAX_OUT})")
+        if self.data_width > MAX_DATA:
+            raise TraceError(f"residual reads {self.data_width} per-point data columns (limit {MAX_DATA})")
         if len(self.blocks) > MAX_BLOCKS:
             raise TraceError(f"residual calls the model {len(self.blocks)} times (supported: 1..{MAX_BLOCKS})")
         for b, blk in enumerate(self.blocks):
@@ -126,7 +129,7 @@ class ResidualProgram:
         self.check_limits()
         s = RProg()
         s.n_instr, s.n_const, s.n_out, s.n_blocks = len(self.instrs), len(self.consts), len(self.outputs), len(self.blocks)
-        s.d, s.n_data = self.d, 0
+        s.d, s.n_data = self.d, self.data_width
         for b, blk in enumerate(self.blocks):
             s.block_J[b] = self.jets_of(b)
             s.block_o[b] = blk.o
@@ -149,7 +152,7 @@ class ResidualProgram:
         regs = self.blocks[b].points
         if regs is None:
             return None
-        sub = eliminate_dead(ResidualProgram(self.d, self.instrs, self.consts, list(regs), []))
+        sub = eliminate_dead(ResidualProgram(self.d, self.instrs, self.consts, list(regs), [], self.data_width))
         if any(op == OP_LOADJ for op, *_ in sub.instrs):
             raise TraceError("model called on points that depend on a model output")
         sub.check_limits()
@@ -176,6 +179,7 @@ class _Tracer:
         self.blocks: List[Block] = []
         # per block: requested derivative level of every (j, k) leaf is implied by j
         self.points: Optional["TMat"] = None
+        self.n_data = 0
 
     def emit(self, op: int, a: int = 0, b: int = 0, c: int = 0) -> int:
         self.instrs.append((op, a, b, c))
@@ -197,6 +201,8 @@ class _Tracer:
         if r is None:
             if key[0] == "x":
                 r = self.emit(OP_LOADX, key[1])
+            elif key[0] == "d":    # column of the per-point data block
+                r = self.emit(OP_LOADD, key[1])
             else:  # ("j", block, j, k) with j in the FULL second-order numbering (0, 1..d, d+1..2d)
                 r = self.emit(OP_LOADJ, key[1], key[2], key[3])
             self._leaf_reg[key] = r
@@ -260,6 +266,26 @@ def _int_exponent(e) -> Optional[int]:
     return None
 
 
+class _Detached:
+    """``u.detach()`` of a traced column.  Its VALUE cannot be used (a detached factor changes the gradient and is
+    not recorded), but user code that only asks for its shape -- ``np.zeros_like(p.cpu().detach().numpy())``,
+    reference examples/navier_stokes_3D_pipe_marching/problem.py:84 -- gets the one-row stand-in of the symbolic
+    batch size, filled with NaN so that any real use shows up in the probe check."""
+
+    def cpu(self): return self
+    def numpy(self): return np.full((1,), np.nan, dtype=np.float32)
+
+    def _bad(self, *a, **k):
+        raise TraceError("detach() inside a residual changes its gradient; not traced")
+
+    __add__ = __radd__ = __sub__ = __rsub__ = __mul__ = __rmul__ = __truediv__ = __rtruediv__ = _bad
+    __neg__ = __pow__ = __rpow__ = __abs__ = __getitem__ = _bad
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        raise TraceError("detach() inside a residual changes its gradient; not traced")
+
+
 class TVar:
     """Symbolic per-point scalar column (what a ``[N]`` tensor is in eager mode)."""
 
@@ -320,7 +346,14 @@ class TVar:
         raise TraceError("comparison of per-point values in residual")
 
     def __len__(self):
-        raise TraceError("len() of a traced column")
+        return 1      # symbolic batch size, see TMat.shape
+
+    @property
+    def shape(self):
+        return (1,)
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
 
     def __getitem__(self, idx):
         raise TraceError("indexing a traced column")
@@ -338,7 +371,10 @@ class TVar:
     def square(self): return self ** 2
     def pow(self, e): return self ** e
     def clone(self): return self
-    def detach(self): raise TraceError("detach() inside a residual changes its gradient; not traced")
+    def cpu(self): return self
+    def to(self, *a, **k): return self
+    def float(self): return self
+    def detach(self): return _Detached()
     def add(self, o): return self + o
     def sub(self, o): return self - o
     def mul(self, o): return self * o
@@ -364,9 +400,17 @@ class TMat:
         self.kind = kind      # "points" | "value" | "grad" | "derived"
         self.block = block
 
+    # The batch size is symbolic.  It answers 1: every tensor user code builds from it (`torch.ones(arg.shape[0])`,
+    # `torch.tensor([-1, 0]).repeat(arg.shape[0], 1)`) then has a leading dimension of one and broadcasts over the
+    # points exactly as its N-row original would -- provided its rows are all equal, which is all that can be said
+    # without data.  Anything else (aranges, random draws, a division by N) makes the traced program differ from
+    # the eager residual at the probe points and is rejected there (`Condition._check_program`).
     @property
     def shape(self):
-        raise TraceError("shape of a traced matrix depends on the batch size")
+        return (1, len(self.cols))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
 
     @property
     def device(self): return self.tr.like.device
@@ -375,7 +419,7 @@ class TMat:
     def dtype(self): return self.tr.like.dtype
 
     def __len__(self):
-        raise TraceError("len() of traced points depends on the batch size")
+        return 1
 
     def __iter__(self):
         raise TraceError("iterating over the rows of a traced matrix")
@@ -425,10 +469,18 @@ class TMat:
     def __mul__(self, o): return self._colwise(o, lambda a, b: a * b)
     def __rmul__(self, o): return self._colwise(o, lambda a, b: b * a)
     def __truediv__(self, o): return self._colwise(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._colwise(o, lambda a, b: b / a)
     def __neg__(self): return TMat(self.tr, [-a for a in self.cols], "derived")
+
+    def sum(self, *a, **k):
+        return _torch_function(torch.sum, (self,) + a, k)
 
     def detach(self):
         raise TraceError("detach() of traced points")
+
+    def to(self, *a, **k): return self
+    def cpu(self): return self
+    def float(self): return self
 
     def requires_grad_(self, *a, **k):
         return self
@@ -444,7 +496,13 @@ _UNARY = {
     torch.neg: OP_NEG, torch.negative: OP_NEG,
 }
 _BIN = {torch.add: OP_ADD, torch.sub: OP_SUB, torch.subtract: OP_SUB, torch.mul: OP_MUL, torch.multiply: OP_MUL,
-        torch.div: OP_DIV, torch.true_divide: OP_DIV, torch.divide: OP_DIV}
+        torch.div: OP_DIV, torch.true_divide: OP_DIV, torch.divide: OP_DIV,
+        # `real_tensor <op> traced` arrives as the Tensor method (the real tensor is args[0])
+        torch.Tensor.add: OP_ADD, torch.Tensor.sub: OP_SUB, torch.Tensor.mul: OP_MUL, torch.Tensor.div: OP_DIV,
+        torch.Tensor.true_divide: OP_DIV, torch.Tensor.__add__: OP_ADD, torch.Tensor.__sub__: OP_SUB,
+        torch.Tensor.__mul__: OP_MUL, torch.Tensor.__truediv__: OP_DIV}
+_BIN_SWAPPED = {torch.Tensor.__radd__: OP_ADD, torch.Tensor.__rsub__: OP_SUB, torch.Tensor.__rmul__: OP_MUL,
+                torch.Tensor.__rtruediv__: OP_DIV}
 
 
 def _first_traced(args):
@@ -467,9 +525,26 @@ def _torch_function(func, args, kwargs):
         kwargs = {k: v for k, v in kwargs.items() if k != "inplace"}
     if func in _UNARY and len(args) == 1 and not kwargs:
         return tr.lift(args[0])._un(_UNARY[func])
-    if func in _BIN and len(args) == 2 and not kwargs:
+    if func is torch.Tensor.to and isinstance(args[0], torch.Tensor):   # real_tensor.to(traced): dtype / device of it
+        return args[0].to(dtype=tr.like.dtype, device=tr.like.device)
+    if func in _BIN_SWAPPED and len(args) == 2 and not kwargs:
+        func, args = {OP_ADD: torch.add, OP_SUB: torch.sub, OP_MUL: torch.mul,
+                      OP_DIV: torch.div}[_BIN_SWAPPED[func]], (args[1], args[0])
+    if func in _BIN and len(args) == 2 and not kwargs and isinstance(args[1], TMat) and not isinstance(args[0], TMat):
+        m = args[1]      # row / scalar <op> traced matrix
+        return {OP_ADD: m.__radd__, OP_SUB: m.__rsub__, OP_MUL: m.__rmul__, OP_DIV: m.__rtruediv__}[_BIN[func]](args[0])
+    if func in _BIN and len(args) == 2 and not kwargs and not isinstance(args[0], TMat):
         return tr.lift(args[0])._bin(_BIN[func], args[1])
-    if func in (torch.pow,) and len(args) == 2:
+    if func in (torch.sum, torch.Tensor.sum) and isinstance(args[0], TMat):
+        dim = args[1] if len(args) > 1 else kwargs.get("dim", kwargs.get("axis"))
+        if dim in (1, -1) and not kwargs.get("keepdim", False):    # sum over the columns: still one value per point
+            cols = [tr.lift(c) for c in args[0].cols]
+            acc = cols[0]
+            for c in cols[1:]:
+                acc = acc + c
+            return acc
+        raise TraceError("sum over the points of a traced matrix")
+    if func in (torch.pow, torch.Tensor.pow, torch.Tensor.__pow__) and len(args) == 2:
         if not isinstance(args[0], TVar):
             raise TraceError("constant ** per-point value")
         return args[0] ** args[1]
@@ -532,6 +607,25 @@ def traced_model_call(engine, arg: TMat) -> TMat:
     return TMat(tr, cols, "value", b)
 
 
+def _is_shift_of(tr: _Tracer, blk: Block, arg: TMat) -> bool:
+    """``model(arg + c)`` differentiated with respect to ``arg`` (reference examples/portal_1D_1C/problem.py:36-39):
+    the shift has an identity Jacobian, so the derivative is the block's own.  True when every coordinate the block
+    was called with is ``arg[:, i] + const`` / ``arg[:, i] - const`` / ``const + arg[:, i]``."""
+    if blk.points is None or len(arg.cols) != tr.d:
+        return False
+    for i, (r, c) in enumerate(zip(blk.points, arg.cols)):
+        if not isinstance(c, TVar):
+            return False
+        op, a, b, _ = tr.instrs[r]
+        is_const = lambda q: tr.instrs[q][0] == OP_CONST   # noqa: E731
+        if op == OP_ADD and ((a == c.reg and is_const(b)) or (b == c.reg and is_const(a))):
+            continue
+        if op == OP_SUB and a == c.reg and is_const(b):
+            continue
+        return False
+    return True
+
+
 def traced_grad(u, arg) -> TMat:
     """``grad(u, arg)`` on traced values (reference condition/diff.py:25-47 semantics, served from jet channels)."""
     from .jet import UnsupportedDerivative
@@ -551,7 +645,7 @@ def traced_grad(u, arg) -> TMat:
         same = _point_regs(tr, arg) == (None if blk.points is None else tuple(blk.points))
     except TraceError:
         same = False
-    if not same:
+    if not same and not _is_shift_of(tr, blk, arg):
         raise UnsupportedDerivative("grad(u, arg): arg is not the tensor the model was called with")
     if j == 0:
         blk.order = max(blk.order, 1)
@@ -576,14 +670,47 @@ def traced_unpack(m) -> tuple:
 
 
 # ---------------------------------------------------------------------------------------------- driver
-def trace_residual(function, model, d: int, like: torch.Tensor) -> ResidualProgram:
-    """Run ``function(model, arg)`` on symbolic points and return the optimised program."""
+def data_columns(item) -> int:
+    """Columns one item of a ConditionExtra data tuple occupies in the packed [N, n_data] block."""
+    if not isinstance(item, torch.Tensor) or item.dim() not in (1, 2) or not item.is_floating_point():
+        raise TraceError("per-point data must be floating-point [N] or [N, c] tensors")
+    return 1 if item.dim() == 1 else int(item.shape[1])
+
+
+def pack_data(items, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The data tuple of a ConditionExtra as one contiguous float32 [N, n_data] block (the layout LOADD reads)."""
+    cols = [t.detach().reshape(n, -1).to(torch.float32) for t in items]
+    if out is None:
+        return torch.cat(cols, dim=1).contiguous()
+    torch.cat(cols, dim=1, out=out)
+    return out
+
+
+def trace_residual(function, model, d: int, like: torch.Tensor, data=None) -> ResidualProgram:
+    """Run ``function(model, arg)`` -- ``function(model, arg, data)`` for a ConditionExtra, ``data`` being a sample
+    of its per-point data tuple that fixes the column layout -- on symbolic points and return the optimised program."""
     tr = _Tracer(d, like)
     pts = TMat(tr, [tr.leaf(("x", i)) for i in range(d)], "points")
     tr.points = pts
     from . import jet
+    extra = ()
+    if data is not None:
+        sym = []
+        for item in data:
+            c = data_columns(item)
+            leaves = [tr.leaf(("d", tr.n_data + i)) for i in range(c)]
+            tr.n_data += c
+            sym.append(leaves[0] if item.dim() == 1 else TMat(tr, leaves, "data"))
+        extra = (tuple(sym),)
+    # a residual that draws random numbers (e.g. num_diff_random's per-point step, reference diff.py:84-111) cannot
+    # be replayed as a fixed program: detected by the generator state moving while it is recorded
+    rng0 = torch.get_rng_state()
+    rng0_cuda = torch.cuda.get_rng_state(like.device) if like.is_cuda else None
     with jet.use_plan(None):
-        res = function(model, pts)
+        res = function(model, pts, *extra)
+    if not torch.equal(rng0, torch.get_rng_state()) or \
+            (rng0_cuda is not None and not torch.equal(rng0_cuda, torch.cuda.get_rng_state(like.device))):
+        raise TraceError("residual draws random numbers")
     if isinstance(res, (TVar, TMat)) or not isinstance(res, (list, tuple)):
         raise TraceError("residual function must return a list of columns")
     outs = []
@@ -591,11 +718,13 @@ def trace_residual(function, model, d: int, like: torch.Tensor) -> ResidualProgr
         if isinstance(r, _Poison):
             r.touch()
         if not isinstance(r, TVar):
-            raise TraceError("residual component is not a traced per-point column")
+            if isinstance(r, (TMat, _Detached)):
+                raise TraceError("residual component is not a traced per-point column")
+            r = tr.lift(r)      # a constant component (a number or a one-element tensor broadcast over the points)
         outs.append(r.reg)
     if not tr.blocks:
         raise TraceError("residual never calls the model")
-    prog = ResidualProgram(d, tr.instrs, tr.consts, outs, tr.blocks)
+    prog = ResidualProgram(d, tr.instrs, tr.consts, outs, tr.blocks, tr.n_data)
     for b in range(len(tr.blocks)):
         prog.points_program(b)      # raises if a block's points depend on a model output
     prog = eliminate_dead(prog)        # (requested-but-unused mixed derivatives must not block the Laplace mode)
@@ -654,7 +783,7 @@ def simplify(prog: ResidualProgram) -> ResidualProgram:
     for blk in prog.blocks:
         if blk.points is not None:
             blk.points = [res(r) for r in blk.points]
-    return ResidualProgram(prog.d, instrs, prog.consts, [res(r) for r in prog.outputs], prog.blocks)
+    return ResidualProgram(prog.d, instrs, prog.consts, [res(r) for r in prog.outputs], prog.blocks, prog.data_width)
 
 
 def eliminate_dead(prog: ResidualProgram) -> ResidualProgram:
@@ -693,7 +822,7 @@ def eliminate_dead(prog: ResidualProgram) -> ResidualProgram:
     for blk in prog.blocks:
         if blk.points is not None:
             blk.points = [remap[r] for r in blk.points]
-    return ResidualProgram(prog.d, instrs, consts, [remap[r] for r in prog.outputs], prog.blocks)
+    return ResidualProgram(prog.d, instrs, consts, [remap[r] for r in prog.outputs], prog.blocks, prog.data_width)
 
 
 def renumber_jets(prog: ResidualProgram) -> ResidualProgram:
@@ -722,7 +851,7 @@ def renumber_jets(prog: ResidualProgram) -> ResidualProgram:
                 raise TraceError("internal: jet channel beyond the block's order")
             b, c = j * blk.o + c, 0
         instrs.append((op, a, b, c))
-    return ResidualProgram(prog.d, instrs, prog.consts, prog.outputs, prog.blocks)
+    return ResidualProgram(prog.d, instrs, prog.consts, prog.outputs, prog.blocks, prog.data_width)
 
 
 # ---------------------------------------------------------------------------------------------- Laplace mode
@@ -880,4 +1009,4 @@ def laplace_rewrite(prog: ResidualProgram) -> ResidualProgram:
     for blk in prog.blocks:
         if blk.points is not None:
             blk.points = [remap[r] for r in blk.points]
-    return ResidualProgram(prog.d, new_instrs, consts, [remap[r] for r in prog.outputs], prog.blocks)
+    return ResidualProgram(prog.d, new_instrs, consts, [remap[r] for r in prog.outputs], prog.blocks, prog.data_width)

@@ -22,8 +22,10 @@ NEG, SIN, COS, EXP, TANH, RELU, ABS, SQRT, LOG = 20, 21, 22, 23, 24, 25, 26, 27,
 POWI, POWF = 30, 31
 
 
-def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds=True):
-    """instrs: list of (op, a, b, c); jets: list of [J, N, o] arrays (one per model call).
+def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds=True, data=None):
+    """instrs: list of (op, a, b, c); jets: list of [J, N, o] arrays (one per model call); data: [N, n_data]
+    per-point auxiliary columns read by LOADD (a ConditionExtra's data tuple, reference
+    condition/condition.py:117-215), or None.
     Returns (values [K, N], sums [K], djets list or None)."""
     x = np.asarray(x)
     dt = x.dtype
@@ -37,6 +39,8 @@ def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds
         elif op == LOADJ:
             o = block_o[a]
             v[i] = np.asarray(jets[a])[b // o, :, b % o].astype(dt)
+        elif op == LOADD:
+            v[i] = np.asarray(data)[:, a].astype(dt)
         elif op == ADD:
             v[i] = v[a] + v[b]
         elif op == SUB:

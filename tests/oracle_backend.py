@@ -54,8 +54,10 @@ class OracleBackend:
         dparams.add_(torch.from_numpy(dp).to(dparams.dtype))
 
     def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
-                         point_major=False, jet_offset=0, jet_stride=0):
+                         point_major=False, jet_offset=0, jet_stride=0, data=None):
         self.calls.append(("resid", int(x.shape[0])))
+        if prog.data_width:
+            assert data is not None and tuple(data.shape) == (x.shape[0], prog.data_width)
         prog.struct()   # exercises the limits / ctypes packing the CUDA backend relies on
         n = int(x.shape[0])
         if jet_stride:     # batched conditions / stacked blocks: this launch works on slices of longer jet blocks
@@ -65,7 +67,8 @@ class OracleBackend:
                 djets = [None if t is None else t[:, o:o + n] for t, o in zip(djets, offs)]
         vals, sm, dj = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
                                    self._np(x), [self._np(j) for j in jets],
-                                   None if weights is None else self._np(weights), want_seeds=djets is not None)
+                                   None if weights is None else self._np(weights), want_seeds=djets is not None,
+                                   data=None if data is None else self._np(data))
         if sums is not None:
             sums.add_(torch.from_numpy(sm).to(sums.dtype))
         if values is not None:

@@ -519,3 +519,135 @@ def test_trainable_fourier_matrix_gradient_matches_oracle(order, lap, cuda_backe
     assert relerr(out.cpu().numpy().transpose(1, 0, 2), ref) < TOL
     assert relerr(dflat, ref_dp) < TOL
     assert relerr(dflat[:nB], ref_dp[:nB]) < TOL and np.abs(ref_dp[:nB]).max() > 0
+
+
+# ------------------------------------------------------------------------------ per-point data (LOADD), 8 blocks
+@pytest.mark.gpu
+def test_residual_kernel_reads_per_point_data_columns(cuda_backend):
+    """ConditionExtra data (reference condition/condition.py:117-215) as LOADD columns of a packed [N, n_data] block:
+    kernel vs numpy interpreter, ragged sizes, seeds included."""
+    model = mp.FNN(2, 1, [64, 64, 64]).cuda()
+
+    def fn(m, a, data):
+        (u,) = mp.unpack(m(a))
+        normal, scale = data
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        return [normal[:, 0] * u_x + normal[:, 1] * u_y - scale, u * scale]
+
+    sample = (torch.zeros(1, 2, device="cuda"), torch.zeros(1, device="cuda"))
+    prog = trace.trace_residual(fn, model, 2, torch.zeros(1, 2, device="cuda"), sample)
+    assert prog.data_width == 3 and prog.struct().n_data == 3
+    for n in (1, 129, 4000):
+        x = torch.rand((n, 2), device="cuda")
+        items = (torch.randn((n, 2), device="cuda", dtype=torch.float64), torch.rand(n, device="cuda"))
+        data = trace.pack_data(items, n)
+        assert data.shape == (n, 3) and data.dtype == torch.float32
+        out, _ = model.jet_engine.forward(x, 1, need_stash=False)
+        dout = torch.empty_like(out)
+        w = torch.tensor([0.7, 1.3], device="cuda")
+        sums = torch.zeros(2, device="cuda")
+        vals = torch.empty((2, n), device="cuda")
+        cuda_backend.residual_program(prog, x, [out], [dout], w, sums, vals, data=data)
+        rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [1], x.cpu().numpy().astype(np.float64),
+                                 [out.cpu().numpy().astype(np.float64)], w.cpu().numpy().astype(np.float64),
+                                 data=data.cpu().numpy().astype(np.float64))
+        assert relerr(vals.cpu().numpy(), rv) < 5e-6, n
+        assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
+        assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n
+    with pytest.raises(AssertionError):
+        cuda_backend.residual_program(prog, x, [out], [dout], w, sums, vals)        # data block missing
+
+
+@pytest.mark.gpu
+def test_condition_extra_trains_on_the_fused_step():
+    """A Neumann-type ConditionExtra next to a plain condition: fused CUDA step (graphs on) against nested autograd of
+    the reference algorithm (oracle port, fp64) -- losses, and weights after 3 Adam steps."""
+    import types
+
+    from oracle import autograd_ref as AR
+    torch.manual_seed(5)
+    model = mp.FNN(2, 1, [64, 64, 64]).cuda()
+
+    def normals(points):
+        p = points.detach()
+        v = torch.stack([torch.cos(3.0 * p[:, 0]), torch.sin(2.0 * p[:, 1]) + 0.5], dim=1)
+        return v / v.norm(dim=1, keepdim=True)
+
+    def make_bc(ns):
+        def fn(m, a, data):
+            (u,) = ns.unpack(m(a))
+            u_x, u_y = ns.unpack(ns.grad(u, a))
+            return [data[0][:, 0] * u_x + data[0][:, 1] * u_y - 0.3]
+        return fn
+
+    def make_in(ns):
+        def fn(m, a):
+            (u,) = ns.unpack(m(a))
+            x, y = ns.unpack(a)
+            u_x, u_y = ns.unpack(ns.grad(u, a))
+            (u_xx, _) = ns.unpack(ns.grad(u_x, a))
+            (_, u_yy) = ns.unpack(ns.grad(u_y, a))
+            return [u_xx + u_yy - torch.sin(x) * y]
+        return fn
+
+    ns = types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack)
+    geo = mp.Hypercube([0, 0], [1, 1])
+    c_in, c_bc = mp.Condition(make_in(ns), geo), mp.ConditionExtra(make_bc(ns), geo, [normals])
+    gen = torch.Generator().manual_seed(0)
+    pts = [torch.rand((300, 2), generator=gen).cuda().requires_grad_(),
+           torch.rand((77, 2), generator=gen).cuda().requires_grad_()]
+    for c, p in zip((c_in, c_bc), pts):
+        c.generator = types.SimpleNamespace(n_points=len(p), generate=lambda cc, m, p=p: p)
+    pinn = mp.PINN(model, [c_in, c_bc])
+    pinn.update_data()
+    ref = AR.MODELS["FNN"](2, 1, hidden_layers=[64, 64, 64]).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in model.state_dict().items()})
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=4, update_grid_every=10**9)
+    fs = tr.fused_step()
+    assert fs is not None and c_bc.program_for(model).data_width == 2, c_bc.trace_note
+    rns = types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack)
+    p64 = [p.detach().cpu().double().requires_grad_() for p in pts]
+    dat = (normals(pts[1]).cpu().double(),)
+    rfns = [make_in(rns), lambda m, a: make_bc(rns)(m, a, dat)]
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for step in range(4):       # two direct runs, then graph replays
+        pinn.select_batch(0)
+        tr._train_batches()
+        total, losses = AR.train_step(ref, ropt, rfns, p64)
+        assert relerr(tr.epoch_loss_detailed.cpu().numpy(), np.asarray([float(v) for v in losses])) < 2e-5, step
+        tr.total_loss, tr.epoch_loss_detailed = 0, None
+    assert fs.graph_replays >= 1
+    rflat = np.concatenate([p.detach().numpy().reshape(-1) for p in ref.parameters()])
+    assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - rflat).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_seven_model_calls_in_one_residual_are_stacked(cuda_backend):
+    """Central second differences in three directions (what Symbols(mode="diff") generates for a 3-D Laplacian,
+    reference condition/symbols.py:188-234, with fixed steps): 7 model calls, one stacked forward and reverse."""
+    torch.manual_seed(2)
+    model = mp.FNN(3, 1, [64, 64, 64]).cuda()
+    h = 2.0 ** -3
+
+    def fn(m, a):
+        f0 = m(a)
+        tot = -6.0 * f0[:, 0]
+        for i in range(3):
+            e = torch.zeros(1, 3, device=a.device)
+            e[0, i] = h
+            tot = tot + m(a + e)[:, 0] + m(a - e)[:, 0]
+        return [tot / (h * h)]
+
+    c = mp.Condition(fn, mp.Hypercube([0, 0, 0], [1, 1, 1]))
+    c.init_output_len(model)
+    prog = c.program_for(model)
+    assert prog is not None and len(prog.blocks) == 7, c.trace_note
+    from multipinn_b200.fused import ConditionRunner
+    r = ConditionRunner(c, prog, model.jet_engine)
+    assert r.stacked
+    x = torch.rand((1000, 3), device="cuda")
+    got = r.residual_values(x)[0]
+    with torch.no_grad():
+        want = fn(model, x)[0]     # eager value-only evaluation of the same stencil
+    assert relerr(got.cpu().numpy(), want.detach().cpu().numpy()) < 1e-4

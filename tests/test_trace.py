@@ -417,3 +417,135 @@ def test_model_calls_of_one_residual_are_stacked_into_one_launch(oracle_backend)
         assert sum(1 for c in oracle_backend.calls if c[0] == "bwd") == len(fs.units)
         assert relerr(tr.epoch_loss_detailed.numpy(), g["losses_f64"]) < 1e-5
         assert relerr(model.jet_engine.flat_grad.numpy(), g["grad_f64"]) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# idioms of the reference's other examples (scripts/example_sweep.py runs all 46 problem.py files; these are the
+# constructs that needed tracer support, pinned here so that they stay on the fused step)
+def _fused_vs_autograd(make, d, n_pts, data_fn=None, hidden=(16, 16), seed=3, shift=None):
+    """Fused step (traced program, oracle backend) vs nested torch autograd of the reference algorithm in fp64."""
+    from oracle import autograd_ref as AR
+    torch.manual_seed(seed)
+    model = mp.FNN(d, 1, list(hidden))
+    ns = types.SimpleNamespace(grad=mp.grad, unpack=mp.unpack)
+    geo = mp.Hypercube([0.0] * d, [1.0] * d)
+    if data_fn is None:
+        cond = mp.Condition(make(ns), geo)
+    else:
+        cond = mp.ConditionExtra(make(ns), geo, [data_fn])
+    pts = torch.rand((n_pts, d), generator=torch.Generator().manual_seed(seed)).requires_grad_()
+    cond.generator = types.SimpleNamespace(n_points=n_pts, generate=lambda c, m: pts)
+    pinn = mp.PINN(model, [cond])
+    pinn.update_data()
+    tr = mp.TrainerOneBatch(pinn, torch.optim.SGD(model.parameters(), lr=0.0), None, num_epochs=1,
+                            update_grid_every=10**9)
+    assert cond.program_for(model) is not None, cond.trace_note
+    assert tr.fused_step() is not None
+    pinn.select_batch(0)
+    tr._train_batches()
+    ref = AR.MODELS["FNN"](d, 1, hidden_layers=list(hidden)).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    rns = types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack)
+    p64 = pts.detach().double().requires_grad_()
+    if data_fn is None:
+        rfn = make(rns)
+    else:
+        dat = tuple(t.double() for t in (data_fn(pts.detach()),))
+        rfn = lambda m, a: make(rns)(m, a, dat)   # noqa: E731
+    total, losses = AR.mean_loss(ref, [rfn], [p64])
+    total.backward()
+    rgrad = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                            for p in ref.parameters()])
+    assert relerr(tr.epoch_loss_detailed.numpy(), losses.detach().numpy()) < 1e-5
+    assert relerr(model.jet_engine.flat_grad.numpy(), rgrad) < 1e-5
+    return cond.program_for(model)
+
+
+def test_tracer_handles_the_idioms_of_the_reference_examples():
+    def make(ns):
+        def fn(m, a):
+            (u,) = ns.unpack(m(a))
+            x, y = ns.unpack(a)
+            # examples/heat_2D_simple/problem.py:31 -- a real 0-d tensor on the LEFT of a traced column
+            c1 = torch.exp(torch.tensor(1)) + 0.5 * y - u
+            # examples/poisson_3D/problem.py:38 -- real tensor * traced column
+            c2 = torch.square(torch.tensor(torch.pi)) * torch.cos(torch.pi * x) - u
+            # examples/laplace_2D_neumann/problem.py:35-43 -- constants sized by the batch, row-wise sum
+            normals = torch.tensor([-1, 0]).repeat(a.shape[0], 1)
+            u_n = torch.sum(ns.grad(u, a) * normals, 1)
+            pi_t = torch.ones_like(y) * np.pi
+            c3 = u_n + (np.pi / (torch.exp(pi_t) - torch.exp(-pi_t))) * (torch.exp(pi_t * y) - torch.exp(-pi_t * y))
+            # examples/navier_stokes_3D_pipe_marching/problem.py:84 -- a constant component shaped after a column
+            c4 = torch.tensor(np.zeros_like(u.cpu().detach().numpy()), dtype=u.dtype)
+            return [c1, c2, c3, c4]
+        return fn
+
+    prog = _fused_vs_autograd(make, 2, 24)
+    assert len(prog.blocks) == 1 and prog.blocks[0].order == 1
+
+
+def test_residuals_that_draw_random_numbers_stay_eager():
+    model = _small_model()
+
+    def fn(m, a):   # num_diff_random's per-point random step (reference condition/diff.py:84-111)
+        f = m(a)
+        (d_x,) = mp.unpack(mp.condition.num_diff_random(m, a, f, torch.tensor([[1.0, 0.0]])))
+        return [d_x]
+
+    c = mp.Condition(fn, mp.Hypercube([0, 0], [1, 1]))
+    c.init_output_len(model)
+    assert c.program_for(model) is None and "random" in c.trace_note
+
+
+def test_derivative_of_a_call_on_shifted_points():
+    """examples/portal_1D_1C/problem.py:33-39: ``ur = model(arg + delta)`` then ``grad(ur, arg)``."""
+    def make(ns):
+        def fn(m, a):
+            (ul,) = ns.unpack(m(a))
+            (ur,) = ns.unpack(m(a + 2 * torch.pi))
+            (ul_x,) = ns.unpack(ns.grad(ul, a))
+            (ur_x,) = ns.unpack(ns.grad(ur, a))
+            (ur_xx,) = ns.unpack(ns.grad(ur_x, a))
+            return [ur - ul, ur_x - ul_x, ur_xx + ur]
+        return fn
+
+    prog = _fused_vs_autograd(make, 1, 20)
+    assert len(prog.blocks) == 2 and prog.blocks[1].points is not None
+    # the eager jet path answers the same (it is what the probe check compared the program with)
+    torch.manual_seed(0)
+    model = mp.FNN(1, 1, [16, 16])
+    x = torch.rand(7, 1).requires_grad_()
+    (ur,) = mp.unpack(model(x + 0.5))
+    (ur_x,) = mp.unpack(mp.grad(ur, x))
+    from oracle import autograd_ref as AR
+    ref = AR.MODELS["FNN"](1, 1, hidden_layers=[16, 16]).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    x64 = x.detach().double().requires_grad_()
+    (rr,) = AR.unpack(ref(x64 + 0.5))
+    (rr_x,) = AR.unpack(AR.grad(rr, x64))
+    assert relerr(ur_x.detach().numpy(), rr_x.detach().numpy()) < 1e-5
+    with pytest.raises(jet.UnsupportedDerivative):     # a scaled argument is not a shift
+        (us,) = mp.unpack(model(x * 2.0))
+        mp.grad(us, x)
+
+
+def test_condition_extra_data_is_traced_as_per_point_columns(oracle_backend):
+    """ConditionExtra (reference condition/condition.py:117-215): the residual takes per-point data -- here a
+    normal field -- which the program reads through LOADD from a packed [N, n_data] block."""
+    def normals(points):
+        p = points.detach()
+        v = torch.stack([torch.cos(3.0 * p[:, 0]), torch.sin(2.0 * p[:, 1]) + 0.5], dim=1)
+        return v / v.norm(dim=1, keepdim=True)
+
+    def make(ns):
+        def fn(m, a, data):
+            (u,) = ns.unpack(m(a))
+            normal = data[0]
+            u_x, u_y = ns.unpack(ns.grad(u, a))
+            return [normal[:, 0] * u_x + normal[:, 1] * u_y - 0.3]     # examples/helmholtz/problem.py:26-29
+        return fn
+
+    prog = _fused_vs_autograd(make, 2, 28, data_fn=normals)
+    assert prog.data_width == 2 and prog.struct().n_data == 2
+    assert any(op == trace.OP_LOADD for op, *_ in prog.instrs)
+    assert any(c[0] == "resid" for c in oracle_backend.calls)

@@ -136,15 +136,18 @@ int mpinn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  *   LOADJ a b      r = jets[a][j][n][k], b = j*o + k   (block a = the a-th model(arg) call)
  *   LOADD a        r = data[n][a]                      (per-point auxiliary data of ConditionExtra, e.g. boundary
  *                                                       normals: reference condition/condition.py:117-215)
- *   ADD SUB MUL DIV a b ;  NEG SIN COS EXP TANH RELU ABS SQRT LOG a ;  POWI a b (integer exponent b) ;
- *   POWF a b (exponent = constant register b)
+ *   ADD SUB MUL DIV MAX MIN a b ;  NEG SIN COS EXP TANH RELU ABS SQRT LOG a ;  POWI a b (integer exponent b) ;
+ *   POWF a b (exponent = constant register b) ;  GT GE a b (1.0 / 0.0 masks: `p > c`) ;
+ *   SEL a b c   r = reg[a] != 0 ? reg[b] : reg[c]   (torch.where, `p[p > c] = 0`: reference
+ *                                                    examples/gas_dynamics_1D/problem.py:33-37)
  * jet_reg[a][j*o+k] is the register that loads that channel, or -1 if the residual does not read it. */
 enum {
   MPINN_RP_CONST = 0, MPINN_RP_LOADX = 1, MPINN_RP_LOADJ = 2, MPINN_RP_LOADD = 3,
-  MPINN_RP_ADD = 10, MPINN_RP_SUB = 11, MPINN_RP_MUL = 12, MPINN_RP_DIV = 13,
+  MPINN_RP_ADD = 10, MPINN_RP_SUB = 11, MPINN_RP_MUL = 12, MPINN_RP_DIV = 13, MPINN_RP_MAX = 14, MPINN_RP_MIN = 15,
   MPINN_RP_NEG = 20, MPINN_RP_SIN = 21, MPINN_RP_COS = 22, MPINN_RP_EXP = 23, MPINN_RP_TANH = 24,
   MPINN_RP_RELU = 25, MPINN_RP_ABS = 26, MPINN_RP_SQRT = 27, MPINN_RP_LOG = 28,
-  MPINN_RP_POWI = 30, MPINN_RP_POWF = 31
+  MPINN_RP_POWI = 30, MPINN_RP_POWF = 31,
+  MPINN_RP_GT = 40, MPINN_RP_GE = 41, MPINN_RP_SEL = 42
 };
 #define MPINN_RP_MAX_INSTR 192
 #define MPINN_RP_MAX_CONST 64

@@ -381,7 +381,10 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, const floa
         ok = in.a >= 0 && in.a < prog->n_blocks && in.b >= 0 && in.b < prog->block_J[in.a] * prog->block_o[in.a];
         break;
       case MPINN_RP_ADD: case MPINN_RP_SUB: case MPINN_RP_MUL: case MPINN_RP_DIV: case MPINN_RP_POWF:
+      case MPINN_RP_MAX: case MPINN_RP_MIN: case MPINN_RP_GT: case MPINN_RP_GE:
         ok = in.a >= 0 && in.a < i && in.b >= 0 && in.b < i; break;
+      case MPINN_RP_SEL:
+        ok = in.a >= 0 && in.a < i && in.b >= 0 && in.b < i && in.c >= 0 && in.c < i; break;
       case MPINN_RP_NEG: case MPINN_RP_SIN: case MPINN_RP_COS: case MPINN_RP_EXP: case MPINN_RP_TANH:
       case MPINN_RP_RELU: case MPINN_RP_ABS: case MPINN_RP_SQRT: case MPINN_RP_LOG: case MPINN_RP_POWI:
         ok = in.a >= 0 && in.a < i; break;

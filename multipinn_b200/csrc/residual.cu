@@ -70,6 +70,13 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
         case MPINN_RP_SUB: r = v[in.a * kResidThreads] - v[in.b * kResidThreads]; break;
         case MPINN_RP_MUL: r = v[in.a * kResidThreads] * v[in.b * kResidThreads]; break;
         case MPINN_RP_DIV: r = v[in.a * kResidThreads] / v[in.b * kResidThreads]; break;
+        case MPINN_RP_MAX: r = fmaxf(v[in.a * kResidThreads], v[in.b * kResidThreads]); break;
+        case MPINN_RP_MIN: r = fminf(v[in.a * kResidThreads], v[in.b * kResidThreads]); break;
+        case MPINN_RP_GT: r = v[in.a * kResidThreads] > v[in.b * kResidThreads] ? 1.0f : 0.0f; break;
+        case MPINN_RP_GE: r = v[in.a * kResidThreads] >= v[in.b * kResidThreads] ? 1.0f : 0.0f; break;
+        case MPINN_RP_SEL:
+          r = v[in.a * kResidThreads] != 0.0f ? v[in.b * kResidThreads] : v[in.c * kResidThreads];
+          break;
         case MPINN_RP_NEG: r = -v[in.a * kResidThreads]; break;
         case MPINN_RP_SIN: r = sinf(v[in.a * kResidThreads]); break;
         case MPINN_RP_COS: r = cosf(v[in.a * kResidThreads]); break;
@@ -117,6 +124,15 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
           *aa += g * inv;
           adj[in.b * kResidThreads] -= g * v[i * kResidThreads] * inv;
         } break;
+        case MPINN_RP_MAX: case MPINN_RP_MIN: {     // the gradient follows the selected operand (a on ties)
+          const float vb = v[in.b * kResidThreads];
+          const bool pick_a = in.op == MPINN_RP_MAX ? va >= vb : va <= vb;
+          if (pick_a) *aa += g; else adj[in.b * kResidThreads] += g;
+        } break;
+        case MPINN_RP_GT: case MPINN_RP_GE: break;  // masks are piecewise constant
+        case MPINN_RP_SEL:                          // (aa is the mask's adjoint here: untouched)
+          if (va != 0.0f) adj[in.b * kResidThreads] += g; else adj[in.c * kResidThreads] += g;
+          break;
         case MPINN_RP_NEG: *aa -= g; break;
         case MPINN_RP_SIN: *aa += g * cosf(va); break;
         case MPINN_RP_COS: *aa -= g * sinf(va); break;

@@ -31,6 +31,8 @@ OP_CONST, OP_LOADX, OP_LOADJ, OP_LOADD = 0, 1, 2, 3
 OP_ADD, OP_SUB, OP_MUL, OP_DIV = 10, 11, 12, 13
 OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_TANH, OP_RELU, OP_ABS, OP_SQRT, OP_LOG = 20, 21, 22, 23, 24, 25, 26, 27, 28
 OP_POWI, OP_POWF = 30, 31
+OP_MAX, OP_MIN = 14, 15                 # element-wise maximum / minimum
+OP_GT, OP_GE, OP_SEL = 40, 41, 42       # a > b, a >= b as 1.0 / 0.0 ;  SEL m x y = x where m != 0 else y
 
 MAX_INSTR, MAX_CONST, MAX_OUT, MAX_BLOCKS, MAX_JO, MAX_DATA = 192, 64, 8, 8, 32, 16
 ORDER_LAPLACE = 3
@@ -39,6 +41,29 @@ ENABLE_LAPLACE = True    # module switch for A/B measurements (bench.py --no-lap
 
 _BINARY = {OP_ADD, OP_SUB, OP_MUL, OP_DIV}
 _UNARY_OPS = {OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_TANH, OP_RELU, OP_ABS, OP_SQRT, OP_LOG}
+_REGS2 = _BINARY | {OP_MAX, OP_MIN, OP_GT, OP_GE, OP_POWF}    # operands a, b are registers
+_REGS1 = _UNARY_OPS | {OP_POWI}                               # operand a is a register
+
+
+def _map_operands(op, a, b, c, f):
+    """(a, b, c) with every REGISTER operand passed through f."""
+    if op in _REGS2:
+        return f(a), f(b), c
+    if op in _REGS1:
+        return f(a), b, c
+    if op == OP_SEL:
+        return f(a), f(b), f(c)
+    return a, b, c
+
+
+def _register_operands(op, a, b, c):
+    if op in _REGS2:
+        return [a, b]
+    if op in _REGS1:
+        return [a]
+    if op == OP_SEL:
+        return [a, b, c]
+    return []
 
 
 class TraceError(Exception):
@@ -336,14 +361,36 @@ class TVar:
     def __bool__(self):
         raise TraceError("residual branches on a per-point value")
 
-    def _cmp(self, o):
-        raise TraceError("comparison of per-point values in residual")
-
-    __lt__ = __le__ = __gt__ = __ge__ = _cmp
+    # comparisons give per-point masks (1.0 / 0.0 columns) for torch.where / masked assignment; using one as a
+    # Python truth value is data-dependent control flow and still raises (__bool__)
+    def __gt__(self, o): return self._bin(OP_GT, o)
+    def __ge__(self, o): return self._bin(OP_GE, o)
+    def __lt__(self, o): return self._bin(OP_GT, o, True)
+    def __le__(self, o): return self._bin(OP_GE, o, True)
     __hash__ = object.__hash__
 
     def __eq__(self, o):
-        raise TraceError("comparison of per-point values in residual")
+        raise TraceError("equality comparison of per-point values in residual")
+
+    def __setitem__(self, mask, value):
+        """``p[p > c] = v`` (reference examples/gas_dynamics_1D/problem.py:33-37): this handle now names the selected
+        column, which is what the in-place write means for everything that uses ``p`` afterwards."""
+        if not isinstance(mask, TVar):
+            raise TraceError("only masked assignment with a traced mask is supported on a traced column")
+        v = self.tr.lift(value)
+        self.reg = self.tr.emit(OP_SEL, mask.reg, v.reg, self.reg)
+        self.leaf = None
+
+    def maximum(self, o): return self._bin(OP_MAX, o)
+    def minimum(self, o): return self._bin(OP_MIN, o)
+
+    def clamp(self, min=None, max=None):
+        r = self
+        if min is not None:
+            r = r._bin(OP_MAX, min)
+        if max is not None:
+            r = r._bin(OP_MIN, max)
+        return r
 
     def __len__(self):
         return 1      # symbolic batch size, see TMat.shape
@@ -548,6 +595,17 @@ def _torch_function(func, args, kwargs):
         if not isinstance(args[0], TVar):
             raise TraceError("constant ** per-point value")
         return args[0] ** args[1]
+    if func in (torch.maximum, torch.minimum) and len(args) == 2 and not kwargs:
+        return tr.lift(args[0])._bin(OP_MAX if func is torch.maximum else OP_MIN, args[1])
+    if func in (torch.clamp, torch.clip) and isinstance(args[0], TVar):
+        lo = args[1] if len(args) > 1 else kwargs.get("min")
+        hi = args[2] if len(args) > 2 else kwargs.get("max")
+        return args[0].clamp(lo, hi)
+    if func is torch.where and len(args) == 3 and not kwargs:
+        if not isinstance(args[0], TVar):
+            raise TraceError("torch.where with a mask that is not a traced comparison")
+        x, y = tr.lift(args[1]), tr.lift(args[2])
+        return TVar(tr, tr.emit(OP_SEL, args[0].reg, x.reg, y.reg))
     if func is torch.square and len(args) == 1:
         return tr.lift(args[0]) ** 2
     if func in (torch.zeros_like, torch.ones_like) and len(args) == 1 and not kwargs:
@@ -752,10 +810,7 @@ def simplify(prog: ResidualProgram) -> ResidualProgram:
         if op == OP_CONST:
             cval[i] = prog.consts[a]
             continue
-        if op in _BINARY or op == OP_POWF:
-            a, b = res(a), res(b)
-        elif op in _UNARY_OPS or op == OP_POWI:
-            a = res(a)
+        a, b, c = _map_operands(op, a, b, c, res)
         instrs[i] = (op, a, b, c)
         ca, cb = cval.get(a) if op in _BINARY else None, cval.get(b) if op in _BINARY else None
         if op == OP_ADD:
@@ -797,13 +852,7 @@ def eliminate_dead(prog: ResidualProgram) -> ResidualProgram:
         if live[r]:
             continue
         live[r] = True
-        op, a, b, c = prog.instrs[r]
-        if op in _BINARY:
-            stack += [a, b]
-        elif op in _UNARY_OPS or op == OP_POWI:
-            stack.append(a)
-        elif op == OP_POWF:
-            stack += [a, b]
+        stack += _register_operands(*prog.instrs[r])
     remap, instrs, consts, cmap = {}, [], [], {}
     for i, (op, a, b, c) in enumerate(prog.instrs):
         if not live[i]:
@@ -813,10 +862,8 @@ def eliminate_dead(prog: ResidualProgram) -> ResidualProgram:
                 cmap[a] = len(consts)
                 consts.append(prog.consts[a])
             a = cmap[a]
-        elif op in _BINARY or op == OP_POWF:
-            a, b = remap[a], remap[b]
-        elif op in _UNARY_OPS or op == OP_POWI:
-            a = remap[a]
+        else:
+            a, b, c = _map_operands(op, a, b, c, remap.__getitem__)
         remap[i] = len(instrs)
         instrs.append((op, a, b, c))
     for blk in prog.blocks:
@@ -923,8 +970,8 @@ def laplace_rewrite(prog: ResidualProgram) -> ResidualProgram:
                 lin[i] = {key: -v for key, v in lin[a].items()}
             if cval[a] is not None:
                 cval[i] = -cval[a]
-        elif op in _UNARY_OPS or op in (OP_POWI, OP_POWF):
-            for r in ((a, b) if op == OP_POWF else (a,)):
+        elif op in _UNARY_OPS or op in (OP_POWI, OP_POWF, OP_MAX, OP_MIN, OP_GT, OP_GE, OP_SEL):
+            for r in _register_operands(op, a, b, c):
                 if lin[r]:
                     for blk in blocks_of(lin[r]):
                         bad[blk] = True
@@ -998,10 +1045,7 @@ def laplace_rewrite(prog: ResidualProgram) -> ResidualProgram:
             else:
                 remap[i] = emit((OP_MUL, const_of(w), lap_leaf[key], 0))
             continue
-        if op in _BINARY or op == OP_POWF:
-            a, b = remap[a], remap[b]
-        elif op in _UNARY_OPS or op == OP_POWI:
-            a = remap[a]
+        a, b, c = _map_operands(op, a, b, c, remap.__getitem__)
         remap[i] = emit((op, a, b, c))
     for blk, cv in weights.items():
         prog.blocks[blk].order = ORDER_LAPLACE

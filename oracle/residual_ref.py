@@ -20,6 +20,8 @@ CONST, LOADX, LOADJ, LOADD = 0, 1, 2, 3
 ADD, SUB, MUL, DIV = 10, 11, 12, 13
 NEG, SIN, COS, EXP, TANH, RELU, ABS, SQRT, LOG = 20, 21, 22, 23, 24, 25, 26, 27, 28
 POWI, POWF = 30, 31
+MAX, MIN = 14, 15
+GT, GE, SEL = 40, 41, 42
 
 
 def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds=True, data=None):
@@ -49,6 +51,16 @@ def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds
             v[i] = v[a] * v[b]
         elif op == DIV:
             v[i] = v[a] / v[b]
+        elif op == MAX:
+            v[i] = np.maximum(v[a], v[b])
+        elif op == MIN:
+            v[i] = np.minimum(v[a], v[b])
+        elif op == GT:
+            v[i] = (v[a] > v[b]).astype(dt)
+        elif op == GE:
+            v[i] = (v[a] >= v[b]).astype(dt)
+        elif op == SEL:      # torch.where(mask, x, y) / p[mask] = value
+            v[i] = np.where(v[a] != 0, v[b], v[c])
         elif op == NEG:
             v[i] = -v[a]
         elif op == SIN:
@@ -98,6 +110,15 @@ def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds
         elif op == DIV:
             adj[a] = adj[a] + g / v[b]
             adj[b] = adj[b] - g * v[i] / v[b]
+        elif op in (MAX, MIN):    # the gradient follows the selected operand (a on ties; torch splits ties evenly)
+            pick_a = (v[a] >= v[b]) if op == MAX else (v[a] <= v[b])
+            adj[a] = adj[a] + np.where(pick_a, g, 0)
+            adj[b] = adj[b] + np.where(pick_a, 0, g)
+        elif op in (GT, GE):
+            pass                   # masks are piecewise constant
+        elif op == SEL:
+            adj[b] = adj[b] + np.where(v[a] != 0, g, 0)
+            adj[c] = adj[c] + np.where(v[a] != 0, 0, g)
         elif op == NEG:
             adj[a] = adj[a] - g
         elif op == SIN:

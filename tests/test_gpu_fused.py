@@ -651,3 +651,36 @@ def test_seven_model_calls_in_one_residual_are_stacked(cuda_backend):
     with torch.no_grad():
         want = fn(model, x)[0]     # eager value-only evaluation of the same stencil
     assert relerr(got.cpu().numpy(), want.detach().cpu().numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_residual_kernel_masks_select_max_min(cuda_backend):
+    """MAX / MIN / GT / GE / SEL (masked assignment, torch.where, clamp) against the numpy interpreter, seeds included."""
+    model = mp.FNN(2, 1, [64, 64, 64]).cuda()
+
+    def fn(m, a):
+        (u,) = mp.unpack(m(a))
+        x, y = mp.unpack(a)
+        p = 0.5 * torch.exp(-x / 0.7)
+        p[p > 0.35] = 0
+        w = torch.where(y <= 0.5, u * 2.0, u - 1.0)
+        c = torch.clamp(u, min=-0.05, max=0.08) + torch.maximum(u, 0.1 * x) - torch.minimum(u, y - 0.5)
+        return [u - p, w, c + torch.where(x >= y, u, -u)]
+
+    prog = trace.trace_residual(fn, model, 2, torch.zeros(1, 2, device="cuda"))
+    ops = {i[0] for i in prog.instrs}
+    assert {trace.OP_GT, trace.OP_GE, trace.OP_SEL, trace.OP_MAX, trace.OP_MIN} <= ops
+    for n in (1, 130, 5000):
+        x = torch.rand((n, 2), device="cuda")
+        out, _ = model.jet_engine.forward(x, 0, need_stash=False)
+        dout = torch.empty_like(out)
+        w = torch.tensor([0.3, 1.0, 2.5], device="cuda")
+        sums = torch.zeros(3, device="cuda")
+        vals = torch.empty((3, n), device="cuda")
+        cuda_backend.residual_program(prog, x, [out], [dout], w, sums, vals)
+        # the interpreter runs in fp32 here: masks must flip at exactly the same points
+        rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [1], x.cpu().numpy(),
+                                 [out.cpu().numpy()], w.cpu().numpy().astype(np.float64))
+        assert relerr(vals.cpu().numpy(), rv) < 5e-6, n
+        assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
+        assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n

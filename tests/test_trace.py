@@ -549,3 +549,32 @@ def test_condition_extra_data_is_traced_as_per_point_columns(oracle_backend):
     assert prog.data_width == 2 and prog.struct().n_data == 2
     assert any(op == trace.OP_LOADD for op, *_ in prog.instrs)
     assert any(c[0] == "resid" for c in oracle_backend.calls)
+
+
+def test_masks_select_and_max_min_are_traced():
+    """Comparison masks, masked assignment (examples/gas_dynamics_1D/problem.py:33-37), torch.where, maximum /
+    minimum / clamp: fused loss and gradient against autograd of the same residual."""
+    def make(ns):
+        def fn(m, a):
+            (u,) = ns.unpack(m(a))
+            x, y = ns.unpack(a)
+            p = 0.5 * torch.exp(-x / 0.7)
+            p[p > 0.35] = 0                                        # masked assignment on a per-point column
+            w = torch.where(y < 0.5, u * 2.0, u - 1.0)             # piecewise residual
+            c = torch.clamp(u, min=-0.05, max=0.08) + torch.maximum(u, 0.1 * x) - torch.minimum(u, y - 0.5)
+            return [u - p, w, c]
+        return fn
+
+    prog = _fused_vs_autograd(make, 2, 64)
+    ops = {i[0] for i in prog.instrs}
+    assert {trace.OP_GT, trace.OP_SEL, trace.OP_MAX, trace.OP_MIN} <= ops
+    # a mask used as a Python truth value is still data-dependent control flow
+    model = _small_model()
+
+    def branching(m, a):
+        (u,) = mp.unpack(m(a))
+        return [u if (u > 0) else -u]
+
+    c = mp.Condition(branching, mp.Hypercube([0, 0], [1, 1]))
+    c.init_output_len(model)
+    assert c.program_for(model) is None and "branches" in c.trace_note

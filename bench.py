@@ -347,19 +347,41 @@ def run_ours(args):
                 bufs[k][i].copy_(h, non_blocking=True)
             ready[k].record(copy_stream)
 
-    def e2e_step(epoch):
+    # The losses of every step are copied to pinned host memory asynchronously and READ one step later (what a
+    # training loop that logs its loss does without stalling the device): the host reads step k's numbers while
+    # step k+1 runs, so the device never waits for the host to prepare the next launch.  The last step's losses are
+    # read inside the timed region too.
+    K1 = 1 + int(trainer.epoch_loss_detailed.numel())
+    host_loss = [torch.empty(K1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]   # step k finished reading bufs[k]
+    loss_log = []
+
+    def read_losses(k):
+        loss_ready[k].synchronize()
+        loss_log.append((float(host_loss[k][0]), host_loss[k][1:].clone()))
+
+    def e2e_step(epoch, first=False):
         k = epoch & 1
         torch.cuda.current_stream().wait_event(ready[k])
         for i in range(len(host_pts)):
             dev_pts[i] = bufs[k][i].detach().requires_grad_()
-        prefetch(k ^ 1)   # (the step that last read that buffer has completed: its losses were read back)
         pinn.update_data()
         step(epoch)
-        return float(trainer.total_loss), trainer.epoch_loss_detailed.cpu()
+        consumed[k].record()
+        host_loss[k][0:1].copy_(trainer.total_loss.detach().reshape(1), non_blocking=True)
+        host_loss[k][1:].copy_(trainer.epoch_loss_detailed.detach().reshape(-1), non_blocking=True)
+        loss_ready[k].record()
+        if not first:
+            read_losses(k ^ 1)            # the previous step's losses (its compute is done or about to be)
+        copy_stream.wait_event(consumed[k ^ 1]) if not first else None
+        prefetch(k ^ 1)                   # next step's points, into the buffer the previous step has finished with
 
     prefetch(epoch & 1)
-    e2e_step(epoch)
+    e2e_step(epoch, first=True)
     epoch += 1
+    torch.cuda.synchronize()
+    loss_log.clear()
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,8 +389,10 @@ def run_ours(args):
     for _ in range(args.steps):
         e2e_step(epoch)
         epoch += 1
+    read_losses((epoch - 1) & 1)          # the last step's losses
     f1.record()
     barrier()
+    assert len(loss_log) == args.steps + 1 and all(l == l for l, _ in loss_log)
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / args.steps
     h2d = sum(p.numel() * 4 for p in host_pts)
     d2h = 4 * (1 + int(trainer.epoch_loss_detailed.numel()))

@@ -89,7 +89,8 @@ int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params
  *   dout    [J,n,o]  gradient w.r.t. the forward's `out`
  *   dparams [P]      ACCUMULATED into (+=); P = number of floats in `params`
  *   dx      [n,d]    written if non-NULL (gradient w.r.t. the points: the `points.grad` the reference's
- *                    `batch_loss.backward()` leaves behind), else skipped; refused for a FOURIER first op */
+ *                    `batch_loss.backward()` leaves behind), else skipped; with a FOURIER first op on the FP32-FMA
+ *                    engine only (forward and reverse with MPINN_ENGINE_FFMA: the tcgen05 reverse kernel refuses it) */
 int mpinn_jet_backward(const mpinn_op_t* ops_host, int n_ops, const float* params,
                        const void* packed, const float* x, int64_t n, int d, int order,
                        const float* lap_coef_host, const float* dout, const void* stash, float* dparams,

@@ -311,8 +311,6 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (n <= 0) return 0;
   if (!params || !packed || !x || !dout || !stash || !dparams || !workspace) return fail("null pointer");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail("packed buffer must be 16-byte aligned");
-  if (dx && ops[0].kind == MPINN_OP_FOURIER)
-    return fail("gradient w.r.t. the points (dx) through a Fourier-feature first op is not implemented");
   if (workspace_bytes < kSkipScratchFloats * sizeof(float)) return fail("backward workspace too small");
   float* skip_scratch = (float*)workspace;                       // first part of the workspace
   workspace = (void*)((float*)workspace + kSkipScratchFloats);   // slabs follow
@@ -327,6 +325,9 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   int rc = 0;
   const bool tc = use_tc(prog, d, order, engine, true, &rc);
   if (rc) return rc;
+  if (tc && dx && ops[0].kind == MPINN_OP_FOURIER)
+    return fail("gradient w.r.t. the points (dx) through a Fourier-feature first op runs on the FP32-FMA engine: "
+                "request MPINN_ENGINE_FFMA for the forward AND the reverse pass (the stash layouts differ)");
   if (tc) {
     e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
                       n_pad, (float*)workspace, slabs, n_params, dparams, dx, skip_scratch, info.sm_count,

@@ -241,9 +241,14 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
         // A frozen encoding needs nothing upstream.  A trainable one (reference fourier_features.py:30-32): bufG holds
         // abar for [sin(xB) | cos(xB)]; both halves flow back into z = xB, and dL/dB[i][f] = sum over points of
         // zbar_0[f] x_i + zbar_{1+i}[f]  (z's first-derivative channel i is B[i][f] itself, the second-order ones 0).
-        if (!(op.flags & MPINN_FLAG_TRAINABLE)) break;
+        // With dx requested the same zbar_0 also gives dL/dx_i = sum_f zbar_0[f] B[i][f] (x enters z_0 = xB only).
+        const bool train = (op.flags & MPINN_FLAG_TRAINABLE) != 0;
+        if (!train && dx == nullptr) break;
         const int m = op.out_dim / 2;
         const float* B = params + op.w_off;
+        float dxp[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) dxp[i] = 0.0f;
         for (int f = g; f < m; f += G) {
           float z[J], as[J], ac[J];
           z[0] = 0.0f;
@@ -262,13 +267,25 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
           }
           act_jets_bwd<D, ORDER>(MPINN_ACT_SINE, z, as, prog.lap_c);
           act_jets_bwd<D, ORDER>(kActCos, z, ac, prog.lap_c);
-          if (valid) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) dxp[i] = fmaf(as[0] + ac[0], __ldg(B + i * m + f), dxp[i]);
+          if (valid && train) {
 #pragma unroll
             for (int i = 0; i < D; ++i) {
               float gb = (as[0] + ac[0]) * xv[i];
               if (ORDER >= 1) gb += as[1 + i] + ac[1 + i];
               atomicAdd(part + op.w_off + i * m + f, gb);
             }
+          }
+        }
+        if (dx != nullptr) {     // sum the G feature groups' partials of every point (bufC is free at op 0)
+#pragma unroll
+          for (int i = 0; i < D; ++i) bufC[(i * G + g) * TPP + p] = dxp[i];
+          __syncthreads();
+          if (g < D && valid) {
+            float s = 0.0f;
+            for (int q = 0; q < G; ++q) s += bufC[(g * G + q) * TPP + p];
+            dx[pt * D + g] = s;
           }
         }
         break;
@@ -314,7 +331,7 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
           }
         }
       }
-      const bool need_dinput = (l > 0) && !(prog.ops[l - 1].kind == MPINN_OP_FOURIER &&
+      const bool need_dinput = (l > 0) && !(prog.ops[l - 1].kind == MPINN_OP_FOURIER && dx == nullptr &&
                                             !(prog.ops[l - 1].flags & MPINN_FLAG_TRAINABLE));
       if (need_dinput) copy_to_smem(Ws, packed + op.pk_bwd, op.out_dim * op.inp);
       __syncthreads();
@@ -360,7 +377,7 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
         atomicAdd(part + op.b_off + f, s);
       }
       // gradient w.r.t. the points: x enters only through the value channel of op 0 (z = W x + b), so
-      // dL/dx_i = sum_o W[o][i] zbar_0[o]  (a Fourier first op is refused at the C ABI)
+      // dL/dx_i = sum_o W[o][i] zbar_0[o]  (a Fourier first op: see its branch above)
       if (l == 0 && dx != nullptr && op.kind == MPINN_OP_LINEAR && g < D && pt < n) {
         float s = 0.0f;
         for (int oo = 0; oo < op.out_dim; ++oo) s = fmaf(__ldg(params + op.w_off + oo * D + g), bufG[oo * TPP + p], s);

@@ -320,6 +320,13 @@ class JetEngine:
             self.packed_valid = True
 
     # ---------------------------------------------------------------- kernels
+    def _engine_id(self) -> int:
+        """Engine both passes of a step run on.  dL/d(points) through a Fourier-feature first op exists on the
+        FP32-FMA engine only (and the two engines' stash layouts differ, so the forward must follow)."""
+        if self.points_grad and int(self.ops[0, 0]) == _lib.OP_FOURIER:
+            return _lib.ENGINE_FFMA
+        return self.kernel_engine
+
     def stash_floats(self, order: int, n: int) -> int:
         return max(backend().stash_bytes(self.ops, self.d, order, n), 4) // 4
 
@@ -333,12 +340,12 @@ class JetEngine:
         if out is None:
             out = torch.empty((self.n_jets(order), n, self.n_out), dtype=torch.float32, device=x.device)
         if stash is None and (need_stash or (x.is_cuda and (order > 0 or self.has_skip)
-                                             and self.kernel_engine != _lib.ENGINE_FFMA and self.tc_supported(order))):
+                                             and self._engine_id() != _lib.ENGINE_FFMA and self.tc_supported(order))):
             # inference (order 0) needs no stash on either engine; value-only passes WITH derivative channels and
             # residual-block programs (their skip scratch lives behind it) stay on the tensor-core engine by
             # passing one
             stash = torch.empty(self.stash_floats(order, n), dtype=torch.float32, device=x.device)
-        b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self.kernel_engine,
+        b.jet_forward(self.ops, self.flat.detach(), self.packed, x, order, out, stash, self._engine_id(),
                       **({"lap": lap} if lap is not None else {}))
         return out, stash
 
@@ -351,7 +358,7 @@ class JetEngine:
     def backward_into(self, x, order, dout, stash, dflat, lap=None, dx=None):
         """dflat [P] += parameter gradient for dL/d(out jets) = dout (one reverse launch + slab fold)."""
         backend().jet_backward(self.ops, self.flat.detach(), self.packed, x, order, dout, stash, dflat,
-                               self._workspace(x.device), self.kernel_engine, dx,
+                               self._workspace(x.device), self._engine_id(), dx,
                                **({"lap": lap} if lap is not None else {}))
 
     def backward(self, x: torch.Tensor, order: int, dout: torch.Tensor, stash: torch.Tensor, want_dx: bool = False,

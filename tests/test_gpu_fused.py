@@ -398,7 +398,7 @@ def test_regularizers_match_reference_on_cuda(kind):
     assert np.abs(model.jet_engine.flat.detach().cpu().numpy() - gr["params_after3"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D"])
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "navier_stokes_2D", "navier_stokes_3D"])
 def test_points_grad_matches_reference_backward_on_cuda(name):
     g = load(name)
     model, conds, pinn = golden_pinn(name, g)

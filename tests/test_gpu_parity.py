@@ -177,12 +177,35 @@ def test_points_gradient_matches_oracle(name, dim, eng):
     assert relerr(dflat.cpu().numpy(), ref_dp) < TOL
 
 
-def test_points_gradient_through_fourier_is_refused():
+@pytest.mark.parametrize("order,lap", [(1, None), (2, None), (3, (1.0, 0.5, 2.0))])
+def test_points_gradient_through_a_fourier_first_op(order, lap):
+    """dL/d(points) through a Fourier-feature encoding (x enters z = xB only): the FP32-FMA engine computes it -- the
+    host selects that engine for both passes when `points_grad` is set -- against the oracle's reverse pass; the tcgen05
+    reverse kernel refuses the request by name instead of returning nothing."""
     m, _, _ = full_model("navier_stokes_3D", 5)
-    x = torch.rand((64, 3), device="cuda")
-    out, stash = m.jet_engine.forward(x, 2, need_stash=True)
+    e = m.jet_engine
+    n = 333
+    rng = np.random.default_rng(5)
+    x_np = rng.random((n, 3), dtype=np.float32) * 0.5
+    x = torch.tensor(x_np).cuda()
+    out, stash = e.forward(x, order, need_stash=True, lap=lap)          # tcgen05 stash
     with pytest.raises(RuntimeError, match="Fourier"):
-        m.jet_engine.backward(x, 2, torch.ones_like(out), stash, want_dx=True)
+        e.backward(x, order, torch.ones_like(out), stash, want_dx=True, lap=lap)
+    e.points_grad = True                                                # -> FP32-FMA engine for both passes
+    assert e._engine_id() == _lib.ENGINE_FFMA
+    out, stash = e.forward(x, order, need_stash=True, lap=lap)
+    dout_np = rng.standard_normal((n, out.shape[0], out.shape[2])).astype(np.float32)
+    dout = torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda()
+    dflat, dx = e.backward(x, order, dout, stash, want_dx=True, lap=lap)
+    prog, flat = AR.build_program(m)
+    _, cache = JR.forward(prog, flat.astype(np.float64), x_np.astype(np.float64), order, lap)
+    ref_dp, ref_dx = JR.backward(prog, flat.astype(np.float64), x_np.astype(np.float64), order, cache,
+                                 dout_np.astype(np.float64), lap)
+    assert relerr(dx.cpu().numpy(), ref_dx) < TOL
+    kind, din, dout_, w_off = (int(v) for v in np.asarray(prog).reshape(-1, 8)[0][:4])
+    assert kind == _lib.OP_FOURIER
+    ref_dp[w_off:w_off + din * (dout_ // 2)] = 0.0      # the encoding matrix is frozen here: no gradient slot is written
+    assert relerr(dflat.cpu().numpy(), ref_dp) < TOL
 
 
 def test_empty_input_is_a_noop():

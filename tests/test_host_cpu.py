@@ -377,7 +377,7 @@ def test_constant_losses(oracle_backend):
         mp.ConstantLosses([1.0])(tr)
 
 
-@pytest.mark.parametrize("name", ["poisson_2D_1C", "burgers_1D", "navier_stokes_2D"])
+@pytest.mark.parametrize("name", ["poisson_2D_1C", "burgers_1D", "navier_stokes_2D", "navier_stokes_3D"])
 def test_points_grad_matches_reference_backward(name, oracle_backend):
     """Opt-in `points_grad`: after backward() every condition's `points.grad` equals what the reference's nested
     autograd leaves there (reference trainer/trainer.py:141 differentiates w.r.t. the points as a side effect;

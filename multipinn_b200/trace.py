@@ -381,6 +381,12 @@ class TVar:
         self.reg = self.tr.emit(OP_SEL, mask.reg, v.reg, self.reg)
         self.leaf = None
 
+    # masks combine like booleans: ~m, m1 & m2, m1 | m2 (torch only defines these on bool tensors, i.e. on masks)
+    def __invert__(self): return self.tr.const(1.0) - self
+    def __and__(self, o): return self * o
+    def __or__(self, o): return self._bin(OP_MAX, o)
+    __rand__, __ror__ = __and__, __or__
+
     def maximum(self, o): return self._bin(OP_MAX, o)
     def minimum(self, o): return self._bin(OP_MIN, o)
 
@@ -417,7 +423,11 @@ class TVar:
     def neg(self): return self._un(OP_NEG)
     def square(self): return self ** 2
     def pow(self, e): return self ** e
-    def clone(self): return self
+    def clone(self):
+        c = TVar(self.tr, self.reg)      # a new handle: masked assignment on the clone must not reach the original
+        c.leaf = self.leaf
+        return c
+
     def cpu(self): return self
     def to(self, *a, **k): return self
     def float(self): return self
@@ -494,7 +504,7 @@ class TMat:
         self.cols[int(k)] = self.tr.lift(value)
 
     def clone(self):
-        return TMat(self.tr, self.cols, self.kind, self.block)
+        return TMat(self.tr, [c.clone() if isinstance(c, TVar) else c for c in self.cols], self.kind, self.block)
 
     # column-wise arithmetic (what `arg + torch.ones_like(arg)` or `arg * 2` mean for an [N, C] tensor)
     def _colwise(self, other, fn):
@@ -762,12 +772,17 @@ def trace_residual(function, model, d: int, like: torch.Tensor, data=None) -> Re
         extra = (tuple(sym),)
     # a residual that draws random numbers (e.g. num_diff_random's per-point step, reference diff.py:84-111) cannot
     # be replayed as a fixed program: detected by the generator state moving while it is recorded
+    import random as _pyrandom
     rng0 = torch.get_rng_state()
     rng0_cuda = torch.cuda.get_rng_state(like.device) if like.is_cuda else None
+    rng0_np, rng0_py = np.random.get_state(), _pyrandom.getstate()
     with jet.use_plan(None):
         res = function(model, pts, *extra)
+    rng1_np = np.random.get_state()
     if not torch.equal(rng0, torch.get_rng_state()) or \
-            (rng0_cuda is not None and not torch.equal(rng0_cuda, torch.cuda.get_rng_state(like.device))):
+            (rng0_cuda is not None and not torch.equal(rng0_cuda, torch.cuda.get_rng_state(like.device))) or \
+            rng0_np[2:] != rng1_np[2:] or not np.array_equal(rng0_np[1], rng1_np[1]) or \
+            rng0_py != _pyrandom.getstate():
         raise TraceError("residual draws random numbers")
     if isinstance(res, (TVar, TMat)) or not isinstance(res, (list, tuple)):
         raise TraceError("residual function must return a list of columns")

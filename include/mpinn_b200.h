@@ -173,6 +173,9 @@ typedef struct mpinn_rprog {
  *                 autograd graph between the residual list and the network outputs)
  *   values[k][n] = r_k[n]                                       (optional: what Condition.get_residual returns;
  *                                                                 values_point_major != 0 stores values[n][k] instead)
+ * point_weights (device [n_out][n], or NULL): per-point loss weights lambda_k[n] -- the loss whose seeds are written
+ * becomes sum_k weights[k] sum_n lambda_k[n] r_k[n]^2 and wsums[k] (device [n_out], or NULL) += sum_n lambda_k[n] r_k[n]^2
+ * (reference regularization/pointwise.py:84-100: a bias-free Linear(N, 1) applied to r**2); sums stays unweighted.
  * data is the device [n, n_data] row-major block LOADD reads (NULL when prog->n_data == 0).
  * prog_host and the two pointer tables are HOST memory; jets[a] / djets[a] are device [J_a, n, o_a] blocks.
  * djets, weights (device [n_out]), sums (device [n_out]) and values may each be NULL.  jet_stride (0 = n) is the
@@ -185,7 +188,7 @@ typedef struct mpinn_rprog {
 int mpinn_residual_program(const mpinn_rprog_t* prog_host, const float* x, const float* data, int64_t n,
                            const float* const* jets_host, float* const* djets_host,
                            const float* weights, float* sums, float* values, int values_point_major,
-                           int64_t jet_stride, void* stream);
+                           int64_t jet_stride, const float* point_weights, float* wsums, void* stream);
 
 /* Adam with its scalar state on the device, so that a captured CUDA graph of the train step can be replayed
  * while the learning rate and the step count change: state = {lr, step, step_size, sqrt(1 - beta2^step)}.

@@ -38,7 +38,7 @@ SIGNATURES = {
                                    c_size_t, c_int, c_void_p]),
     "mpinn_engine_supports": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
     "mpinn_residual_program": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+                                       c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mpinn_adam_tick": (c_int, [c_void_p, c_float, c_float, c_void_p]),
     "mpinn_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float,
                                     c_float, c_float, c_float, c_void_p]),

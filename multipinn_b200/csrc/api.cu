@@ -35,7 +35,8 @@ cudaError_t read_tc_debug_fwd(long long* out, int n);
 cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, const float* data, int64_t n,
                             const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
-                            int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream);
+                            int values_point_major, int64_t jet_stride, const float* point_weights, float* wsums,
+                            int sm_count, cudaStream_t stream);
 cudaError_t launch_adam_tick(float* state, float beta1, float beta2, cudaStream_t stream);
 cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* state,
                             float beta1, float beta2, float eps, float grad_scale, cudaStream_t stream);
@@ -352,7 +353,8 @@ int mpinn_engine_supports(const mpinn_op_t* ops, int n_ops, int d, int order, in
 
 int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, const float* data, int64_t n,
                            const float* const* jets, float* const* djets, const float* weights, float* sums, float* values,
-                           int values_point_major, int64_t jet_stride, void* stream) {
+                           int values_point_major, int64_t jet_stride, const float* point_weights, float* wsums,
+                           void* stream) {
   if (!prog || !x) return fail("null pointer");
   if (prog->n_blocks > 0 && !jets) return fail("residual program: null jet table");
   if (prog->n_blocks == 0 && djets) return fail("residual program: seeds requested without model calls");
@@ -399,7 +401,7 @@ int mpinn_residual_program(const mpinn_rprog_t* prog, const float* x, const floa
   cudaError_t e = device_info(&info);
   if (e != cudaSuccess) return fail_cuda("device query", e);
   e = launch_residual(*prog, x, data, n, jets, djets, weights, sums, values, values_point_major, jet_stride,
-                      info.sm_count, (cudaStream_t)stream);
+                      point_weights, wsums, info.sm_count, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("residual_program", e);
   return 0;
 }

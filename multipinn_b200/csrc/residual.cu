@@ -21,6 +21,8 @@ constexpr int kResidThreads = 128;
 struct ResidIO {
   const float* jets[MPINN_RP_MAX_BLOCKS];
   float* djets[MPINN_RP_MAX_BLOCKS];
+  const float* point_weights;   // [n_out][n] per-point loss weights lambda_k[n] (PointwiseLosses), or NULL
+  float* wsums;                 // [n_out] += sum_n lambda_k[n] r_k[n]^2, or NULL
 };
 
 __device__ __forceinline__ float powi(float v, int k) {
@@ -48,9 +50,13 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
   float acc[MPINN_RP_MAX_OUT];
 #pragma unroll
   for (int k = 0; k < MPINN_RP_MAX_OUT; ++k) acc[k] = 0.0f;
-  float wk[MPINN_RP_MAX_OUT];
+  float wk[MPINN_RP_MAX_OUT], accw[MPINN_RP_MAX_OUT];
 #pragma unroll
-  for (int k = 0; k < MPINN_RP_MAX_OUT; ++k) wk[k] = (SEEDS && k < prog.n_out) ? (weights ? __ldg(weights + k) : 1.0f) : 0.0f;
+  for (int k = 0; k < MPINN_RP_MAX_OUT; ++k) {
+    wk[k] = (SEEDS && k < prog.n_out) ? (weights ? __ldg(weights + k) : 1.0f) : 0.0f;
+    accw[k] = 0.0f;
+  }
+  const float* __restrict__ pwts = io.point_weights;
 
   for (int64_t pt = (int64_t)blockIdx.x * kResidThreads + t; pt < n; pt += (int64_t)gridDim.x * kResidThreads) {
     // ---------------------------------------------------------------- forward sweep
@@ -98,9 +104,11 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
       if (k < prog.n_out) {
         const int reg = prog.out_reg[k];
         const float r = v[reg * kResidThreads];
+        const float pw = pwts ? __ldg(pwts + (int64_t)k * n + pt) : 1.0f;
         acc[k] = fmaf(r, r, acc[k]);
+        accw[k] = fmaf(pw * r, r, accw[k]);
         if (values) values[values_point_major ? pt * prog.n_out + k : (int64_t)k * n + pt] = r;
-        if (SEEDS) adj[reg * kResidThreads] += 2.0f * wk[k] * r;
+        if (SEEDS) adj[reg * kResidThreads] += 2.0f * wk[k] * pw * r;
       }
     }
     if (!SEEDS) continue;
@@ -159,6 +167,26 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
     }
   }
 
+  if (io.wsums != nullptr) {      // weighted sums first (same reduction, separate scratch)
+    __shared__ float redw[MPINN_RP_MAX_OUT][kResidThreads / 32];
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int k = 0; k < MPINN_RP_MAX_OUT; ++k) {
+      if (k < prog.n_out) {
+        float s = accw[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) redw[k][warp] = s;
+      }
+    }
+    __syncthreads();
+    if (t < prog.n_out) {
+      float s = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kResidThreads / 32; ++w) s += redw[t][w];
+      atomicAdd(io.wsums + t, s);
+    }
+  }
   if (sums != nullptr) {
     __shared__ float red[MPINN_RP_MAX_OUT][kResidThreads / 32];
     const int lane = t & 31, warp = t >> 5;
@@ -184,9 +212,12 @@ residual_kernel(const __grid_constant__ mpinn_rprog_t prog, const ResidIO io, co
 cudaError_t launch_residual(const mpinn_rprog_t& prog, const float* x, const float* data, int64_t n,
                             const float* const* jets,
                             float* const* djets, const float* weights, float* sums, float* values,
-                            int values_point_major, int64_t jet_stride, int sm_count, cudaStream_t stream) {
+                            int values_point_major, int64_t jet_stride, const float* point_weights, float* wsums,
+                            int sm_count, cudaStream_t stream) {
   const int64_t jstride = jet_stride > 0 ? jet_stride : n;
   ResidIO io;
+  io.point_weights = point_weights;
+  io.wsums = wsums;
   for (int b = 0; b < MPINN_RP_MAX_BLOCKS; ++b) {
     io.jets[b] = (b < prog.n_blocks && jets) ? jets[b] : nullptr;
     io.djets[b] = (b < prog.n_blocks && djets) ? djets[b] : nullptr;

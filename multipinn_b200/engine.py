@@ -114,7 +114,7 @@ class CudaBackend:
         CudaBackend.gpu_launches += 2
 
     def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
-                         point_major=False, jet_offset=0, jet_stride=0, data=None):
+                         point_major=False, jet_offset=0, jet_stride=0, data=None, point_weights=None, wsums=None):
         """One launch: residual components of a traced program at the points ``x``; ``sums[k] += sum r_k^2``,
         ``djets[b]`` = seeds of the reverse pass for ``sum_k weights[k] sum_n r_k^2``, ``values[k, n] = r_k``
         (``values[n, k]`` with ``point_major``).  ``jet_offset`` / ``jet_stride``: the jet blocks hold ``jet_stride``
@@ -131,6 +131,8 @@ class CudaBackend:
             dp = (ctypes.c_void_p * nb)(*[(t.data_ptr() + o if t is not None else 0) for t, o in zip(djets, offs)])
         for t in list(jets) + [t for t in (djets or []) if t is not None]:
             assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+        if point_weights is not None:
+            assert tuple(point_weights.shape) == (len(prog.outputs), x.shape[0]) and point_weights.dtype == torch.float32
         if prog.data_width:
             assert data is not None and tuple(data.shape) == (x.shape[0], prog.data_width) \
                 and data.dtype == torch.float32, "per-point data block must be float32 [N, n_data]"
@@ -138,7 +140,8 @@ class CudaBackend:
         _lib.check(self.lib.mpinn_residual_program(ctypes.byref(st), self._ptr(x),
                                                    self._ptr(data if prog.data_width else None), x.shape[0], jp, dp,
                                                    self._ptr(weights), self._ptr(sums), self._ptr(values),
-                                                   1 if point_major else 0, int(jet_stride), self._stream()),
+                                                   1 if point_major else 0, int(jet_stride),
+                                                   self._ptr(point_weights), self._ptr(wsums), self._stream()),
                    "mpinn_residual_program")
         self._timed_end(tok)
         CudaBackend.gpu_launches += 1

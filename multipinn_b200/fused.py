@@ -37,6 +37,9 @@ class ConditionRunner:
         self.x = None
         self.data = None            # [n, n_data] per-point data block of a ConditionExtra (LOADD)
         self._data_src = None
+        # PointwiseLosses: lambda_k[n] (read), r_k[n] (written every step: the ascent direction r^2) and the slice of
+        # the weighted-sum accumulators; all None otherwise
+        self.lam = self.vals = self.wsums = None
         self.blocks: List[_BlockBuffers] = []
         for b, blk in enumerate(prog.blocks):
             bb = _BlockBuffers()
@@ -82,8 +85,9 @@ class ConditionRunner:
 
     def launch_residual_shared(self, weights, sums):
         g = self.group
-        backend().residual_program(self.prog, self.x, [g.out], [g.dout], weights, sums,
-                                   jet_offset=self.n0, jet_stride=g.n_total, data=self.data)
+        backend().residual_program(self.prog, self.x, [g.out], [g.dout], weights, sums, self.vals,
+                                   jet_offset=self.n0, jet_stride=g.n_total, data=self.data,
+                                   point_weights=self.lam, wsums=self.wsums)
 
     def bind(self, n: int, device) -> bool:
         """(Re)allocate the static buffers for n points; True if they changed (a captured graph is then stale)."""
@@ -128,13 +132,15 @@ class ConditionRunner:
                     be.residual_program(bb.points_prog, self.x, [], None, None, None, bb.x, point_major=True,
                                         data=self.data)
             eng.forward(self.xcat, bb0.order, True, lap=bb0.lap, out=self.out_cat, stash=self.stash_cat)
-            be.residual_program(self.prog, self.x, [self.out_cat] * B, [self.dout_cat] * B, weights, sums,
-                                jet_offset=[b * n for b in range(B)], jet_stride=B * n, data=self.data)
+            be.residual_program(self.prog, self.x, [self.out_cat] * B, [self.dout_cat] * B, weights, sums, self.vals,
+                                jet_offset=[b * n for b in range(B)], jet_stride=B * n, data=self.data,
+                                point_weights=self.lam, wsums=self.wsums)
             eng.backward_into(self.xcat, bb0.order, self.dout_cat, self.stash_cat, dflat, lap=bb0.lap)
             return
         self._forward_blocks(self.x, self.blocks, True, self.data)
         backend().residual_program(self.prog, self.x, [bb.out for bb in self.blocks],
-                                   [bb.dout for bb in self.blocks], weights, sums, data=self.data)
+                                   [bb.dout for bb in self.blocks], weights, sums, self.vals, data=self.data,
+                                   point_weights=self.lam, wsums=self.wsums)
         for bb in self.blocks:
             eng.backward_into(bb.x, bb.order, bb.dout, bb.stash, dflat, lap=bb.lap)
 
@@ -208,6 +214,7 @@ class FusedStep:
         self.mode = mode
         self.reg = reg
         self.per_condition = mode in ("gradient", "normal")
+        self.trainer = None           # set by build(): the pointwise policy follows the trainer's epoch counter
         self.flat_adam = flat_adam
         self.runners: List[ConditionRunner] = [ConditionRunner(c, p, engine) for c, p in zip(conditions, programs)]
         self.K = sum(r.K for r in self.runners)
@@ -245,7 +252,7 @@ class FusedStep:
         eng = trainer._engine
         if eng is None or eng.points_grad or trainer.num_batches < 1:
             return None
-        from .regularization import ConstantLosses, GradientLosses, NormalLosses
+        from .regularization import ConstantLosses, GradientLosses, NormalLosses, PointwiseLosses
         from .trainer.trainer import Trainer
         reg = None
         if trainer.calc_loss == Trainer.mean_calc_loss:
@@ -255,6 +262,9 @@ class FusedStep:
         elif type(trainer.calc_loss) in (ConstantLosses, GradientLosses, NormalLosses):
             reg = trainer.calc_loss
             mode = {ConstantLosses: "constant", GradientLosses: "gradient", NormalLosses: "normal"}[type(reg)]
+        elif type(trainer.calc_loss) is PointwiseLosses and trainer.calc_loss.optimizer_def is torch.optim.Adam \
+                and trainer.num_batches == 1 and not trainer.calc_loss.models:
+            reg, mode = trainer.calc_loss, "pointwise"
         else:
             return None
         progs = []
@@ -275,8 +285,11 @@ class FusedStep:
             return None
         if mode in ("gradient", "normal") and (K != len(progs) or K < 2):
             return None
-        return FusedStep(eng, trainer.pinn.conditions, progs, mode, trainer._flat_adam,
-                         use_graphs=getattr(trainer, "use_cuda_graphs", True), reg=reg)
+        fs = FusedStep(eng, trainer.pinn.conditions, progs, mode, trainer._flat_adam,
+                       use_graphs=getattr(trainer, "use_cuda_graphs", True), reg=reg)
+        import weakref
+        fs.trainer = weakref.ref(trainer)
+        return fs
 
     # ------------------------------------------------------------------ buffers
     def _bind(self, device):
@@ -306,6 +319,9 @@ class FusedStep:
             elif self.mode == "constant":  # total = sum_k lambda_k mean_n r^2     (reference regularization/constant.py)
                 self.lambdas = torch.tensor([float(v) for v in self.reg.lambdas], dtype=torch.float32, device=device)
                 self.weights = self.inv_counts * self.lambdas
+            elif self.mode == "pointwise":   # total = sum_k sum_n lambda_kn r_kn^2  (reference pointwise.py:84-100)
+                self.weights = torch.ones(K, dtype=torch.float32, device=device)
+                self._pw_allocate(device)
             else:                        # total = sum_k mean_n r^2                (reference trainer.py:155-167)
                 self.weights = self.inv_counts.clone()  # (gradient / normal: per-condition means, combined below)
             if self.per_condition:
@@ -336,12 +352,90 @@ class FusedStep:
         return eng.comm_buffer(self.K + 1)[P:P + self.K + 1]   # [K component means, total]
 
     # ------------------------------------------------------------------ launches
+    # ------------------------------------------------------------------ PointwiseLosses (per-point loss weights)
+    def _pw_allocate(self, device):
+        """Flat buffers over all (component, point) pairs: lambda, the residual values of the last step, Adam moments
+        and the ascent direction; every runner works on its [K_r, n_r] views."""
+        total = sum(r.K * r.n for r in self.runners)
+        self.pw_lam = torch.ones(total, dtype=torch.float32, device=device)
+        self.pw_vals = torch.zeros(total, dtype=torch.float32, device=device)
+        self.pw_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self.pw_m = torch.zeros(total, dtype=torch.float32, device=device)
+        self.pw_v = torch.zeros(total, dtype=torch.float32, device=device)
+        self.pw_train = torch.ones(total, dtype=torch.float32, device=device)    # 0 on ignored components
+        self.pw_state = torch.zeros(4, dtype=torch.float32, device=device)
+        self.wsums = torch.zeros(self.K, dtype=torch.float32, device=device)
+        off = 0
+        for r, k0 in zip(self.runners, self.k0):
+            m = r.K * r.n
+            r.lam = self.pw_lam[off:off + m].view(r.K, r.n)
+            r.vals = self.pw_vals[off:off + m].view(r.K, r.n)
+            r.wsums = self.wsums[k0:k0 + r.K]
+            off += m
+        self._pw_calls = 0
+        self._pw_live = False
+        self.reg.models = []      # (re)built against the new buffers at the next call
+
+    def _pw_sync_policy(self):
+        """Host side of PointwiseLosses.__call__ (reference pointwise.py:36-100, 117-152) before the launches: the reset
+        at grid updates, the first launch (weights = bias-free Linear(N, 1) modules filled with 1, here views of the
+        flat lambda buffer), and which optimizer is the one being stepped.  Quirk kept: after a grid update the new
+        weight modules get a NEW optimizer appended while optimizers[current_batch] -- the first one -- keeps being
+        stepped, so only the first generation of weights is ever trained."""
+        reg, tr = self.reg, self.trainer()
+        if tr.current_epoch % tr.update_grid_every == 0 and tr.current_batch == 0:
+            reg.ignored_mask = None
+            reg.models = []
+        if len(reg.models) < 1:
+            reg.models.append([])
+            reg.ignored_mask = []
+            self.pw_lam.fill_(1.0)
+            self.pw_train.fill_(1.0)
+            off, index = 0, 0
+            for r in self.runners:
+                for k in range(r.K):
+                    if index in reg.ignored_indexes:
+                        reg.ignored_mask.append(True)
+                        reg.models[0].append(None)
+                        self.pw_train[off:off + r.n] = 0.0
+                    else:
+                        reg.ignored_mask.append(False)
+                        lin = torch.nn.Linear(r.n, 1, bias=False, device=self.pw_lam.device)
+                        lin.weight.data = self.pw_lam[off:off + r.n].view(1, r.n)
+                        reg.models[0].append(lin)
+                    off += r.n
+                    index += 1
+            reg.optimizers.append(("fused-adam-ascent", self.pw_state, self.pw_m, self.pw_v))
+            live = len(reg.optimizers) == 1
+            if live:
+                self.pw_m.zero_()
+                self.pw_v.zero_()
+                self.pw_state.zero_()
+                self.pw_state[0] = float(reg.lr)
+            self._pw_calls = 0
+            if live != self._pw_live or not live:
+                self._g_compute = None                      # the captured sequence changes
+                self._calls["_g_compute"] = 0
+            self._pw_live = live
+
+    def _pw_ascent(self):
+        """lambda <- Adam(maximize=True, lr) step on d total / d lambda = r^2 of the previous evaluation."""
+        be = backend()
+        torch.mul(self.pw_vals, self.pw_vals, out=self.pw_g)
+        self.pw_g.mul_(self.pw_train)
+        be.adam_tick(self.pw_state, 0.9, 0.999)
+        be.adam_step_dev(self.pw_lam, self.pw_g, self.pw_m, self.pw_v, self.pw_state, 0.9, 0.999, 1e-8, -1.0)
+
     def _compute(self):
         eng = self.engine
         eng.flat_grad.zero_()
         self.sums.zero_()
         if self.per_condition:
             self.G.zero_()
+        if self.mode == "pointwise":
+            self.wsums.zero_()
+            if self._pw_live and self._pw_calls > 0:
+                self._pw_ascent()
         for u in self.units:
             if isinstance(u, BatchedGroup):
                 u.launch(self.weights, self.sums, eng.flat_grad, [self.k0[self.runners.index(m)] for m in u.members])
@@ -357,6 +451,9 @@ class FusedStep:
             torch.sum(lv[:K], dim=0, out=lv[K])
             return
         torch.mul(self.sums, self.inv_counts, out=lv[:K])
+        if self.mode == "pointwise":     # reported: unweighted means; optimised: the weighted sums
+            torch.sum(self.wsums, dim=0, out=lv[K])
+            return
         if self.mode == "mean":
             torch.mul(torch.sum(self.sums), self.inv_total, out=lv[K])
         elif self.mode == "legacy":
@@ -420,7 +517,11 @@ class FusedStep:
         for r in self.runners:
             r.load_batch()
         self.engine._ensure_packed()
+        if self.mode == "pointwise":
+            self._pw_sync_policy()
         self._graphed("_g_compute", self._compute)
+        if self.mode == "pointwise":
+            self._pw_calls += 1
 
     def update(self, grad_scale: float = 1.0) -> bool:
         """Optimizer step on the device; False if the optimizer is not the fused Adam (caller steps it)."""

@@ -24,7 +24,7 @@ MAX, MIN = 14, 15
 GT, GE, SEL = 40, 41, 42
 
 
-def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds=True, data=None):
+def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds=True, data=None, point_weights=None):
     """instrs: list of (op, a, b, c); jets: list of [J, N, o] arrays (one per model call); data: [N, n_data]
     per-point auxiliary columns read by LOADD (a ConditionExtra's data tuple, reference
     condition/condition.py:117-215), or None.
@@ -91,8 +91,9 @@ def evaluate(instrs, consts, outputs, block_o, x, jets, weights=None, want_seeds
         return values, sums, None
     w = np.ones(len(outputs)) if weights is None else np.asarray(weights, dtype=np.float64)
     adj = [np.zeros(N, dtype=dt) for _ in instrs]
-    for k, r in enumerate(outputs):
-        adj[r] = adj[r] + 2.0 * w[k] * v[r]
+    for k, r in enumerate(outputs):     # point_weights [K, N]: lambda_k[n] of PointwiseLosses (loss = sum w_k lambda r^2)
+        pw = 1.0 if point_weights is None else np.asarray(point_weights)[k].astype(dt)
+        adj[r] = adj[r] + 2.0 * w[k] * pw * v[r]
     for i in range(len(instrs) - 1, -1, -1):
         op, a, b, c = instrs[i]
         g = adj[i]

@@ -54,7 +54,7 @@ class OracleBackend:
         dparams.add_(torch.from_numpy(dp).to(dparams.dtype))
 
     def residual_program(self, prog, x, jets, djets=None, weights=None, sums=None, values=None,
-                         point_major=False, jet_offset=0, jet_stride=0, data=None):
+                         point_major=False, jet_offset=0, jet_stride=0, data=None, point_weights=None, wsums=None):
         self.calls.append(("resid", int(x.shape[0])))
         if prog.data_width:
             assert data is not None and tuple(data.shape) == (x.shape[0], prog.data_width)
@@ -68,7 +68,11 @@ class OracleBackend:
         vals, sm, dj = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [b.o for b in prog.blocks],
                                    self._np(x), [self._np(j) for j in jets],
                                    None if weights is None else self._np(weights), want_seeds=djets is not None,
-                                   data=None if data is None else self._np(data))
+                                   data=None if data is None else self._np(data),
+                                   point_weights=None if point_weights is None else self._np(point_weights))
+        if wsums is not None:
+            pw = 1.0 if point_weights is None else self._np(point_weights).astype(np.float64)
+            wsums.add_(torch.from_numpy((pw * vals.astype(np.float64) ** 2).sum(axis=1)).to(wsums.dtype))
         if sums is not None:
             sums.add_(torch.from_numpy(sm).to(sums.dtype))
         if values is not None:

@@ -383,6 +383,7 @@ def test_regularizers_match_reference_on_cuda(kind):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     reg = mp.NormalLosses(alpha=0.9) if kind == "normal" else mp.PointwiseLosses(ignored_indexes=[1], lr=0.01)
     tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    assert tr.fused_step() is not None      # both are loss policies of the fused step (the third step is a graph replay)
     for e in range(3):
         tr.current_epoch = e + 1
         tr._train_epoch()
@@ -683,4 +684,34 @@ def test_residual_kernel_masks_select_max_min(cuda_backend):
                                  [out.cpu().numpy()], w.cpu().numpy().astype(np.float64))
         assert relerr(vals.cpu().numpy(), rv) < 5e-6, n
         assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
+        assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n
+
+
+@pytest.mark.gpu
+def test_residual_kernel_per_point_loss_weights(cuda_backend):
+    """point_weights / wsums of mpinn_residual_program (PointwiseLosses: loss = sum_k sum_n lambda_kn r_kn^2):
+    seeds, weighted and unweighted sums against the numpy interpreter."""
+    model = mp.FNN(2, 2, [64, 64, 64]).cuda()
+
+    def fn(m, a):
+        u, v = mp.unpack(m(a))
+        x, y = mp.unpack(a)
+        u_x, u_y = mp.unpack(mp.grad(u, a))
+        return [u_x + v * torch.sin(x), u_y - u * y]
+
+    prog = trace.trace_residual(fn, model, 2, torch.zeros(1, 2, device="cuda"))
+    for n in (1, 131, 6000):
+        x = torch.rand((n, 2), device="cuda")
+        out, _ = model.jet_engine.forward(x, 1, need_stash=False)
+        dout = torch.empty_like(out)
+        lam = torch.rand((2, n), device="cuda") * 3.0
+        sums, wsums = torch.zeros(2, device="cuda"), torch.zeros(2, device="cuda")
+        vals = torch.empty((2, n), device="cuda")
+        cuda_backend.residual_program(prog, x, [out], [dout], None, sums, vals, point_weights=lam, wsums=wsums)
+        rv, rs, rd = RR.evaluate(prog.instrs, prog.consts, prog.outputs, [2], x.cpu().numpy().astype(np.float64),
+                                 [out.cpu().numpy().astype(np.float64)], None,
+                                 point_weights=lam.cpu().numpy().astype(np.float64))
+        assert relerr(vals.cpu().numpy(), rv) < 5e-6, n
+        assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
+        assert relerr(wsums.cpu().numpy(), (lam.cpu().numpy().astype(np.float64) * rv ** 2).sum(axis=1)) < 5e-6, n
         assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n

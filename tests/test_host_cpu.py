@@ -339,21 +339,27 @@ def test_normal_losses_matches_reference(oracle_backend):
     assert np.abs(model.jet_engine.flat.detach().numpy() - gr["params_after3"]).max() < 2e-5
 
 
-def test_pointwise_losses_matches_reference(oracle_backend):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "eager"])
+def test_pointwise_losses_matches_reference(fused, oracle_backend):
     """PointwiseLosses(ignored_indexes=[1], lr=0.01): per-point weights after each maximising Adam step, weighted
-    totals, reported losses and network weights over 3 steps (reference regularization/pointwise.py:9-152); the
-    residuals are evaluated once per step here (one forward per condition)."""
+    totals, reported losses and network weights over 3 steps (reference regularization/pointwise.py:9-152).  On the
+    fused step the weights are an input of the residual launch (seeds 2 lambda r, sum lambda r^2 accumulated next to
+    sum r^2) and their Adam ascent runs on the device; on the eager path the residuals are evaluated once per step
+    (one forward per condition)."""
     g = load("poisson_2D_1C")
     gr = np.load(os.path.join(os.path.dirname(__file__), "golden", "poisson_pointwise_reg.npz"))
     model, conds, pinn = build_pinn("poisson_2D_1C", g)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     reg = mp.PointwiseLosses(ignored_indexes=[1], lr=0.01)
     tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
+    tr.use_fused_step = fused
+    assert (tr.fused_step() is not None) == fused
     for e in range(3):
         tr.current_epoch = e + 1
         oracle_backend.calls.clear()
         tr._train_epoch()
-        assert sum(1 for c in oracle_backend.calls if c[0] == "fwd") == len(conds)
+        n_fwd = sum(1 for c in oracle_backend.calls if c[0] == "fwd")
+        assert n_fwd == (2 if fused else len(conds))      # fused: domain + the four boundary conditions batched
         ms = reg.models[0]
         assert ms[1] is None and reg.ignored_mask[1]
         lam = np.concatenate([ms[0].weight.detach().numpy().reshape(-1)[:16],
@@ -562,3 +568,30 @@ def test_trainable_fourier_matrix_gets_a_gradient(oracle_backend):
     assert relerr(model.jet_engine.flat_grad.numpy(), rgrad) < 1e-5
     assert float(model.jet_engine.flat_grad[:B0.numel()].abs().max()) > 0
     assert not torch.equal(model.fourier_encoding.B.detach(), B0)          # B is trained
+
+
+def test_pointwise_fused_follows_the_grid_update_quirk(oracle_backend):
+    """After a grid update the reference rebuilds the weight modules (lambda = 1) but keeps stepping the FIRST
+    optimizer (reference pointwise.py:60-66, 137-152), so only the first generation of weights is ever trained.  The
+    fused policy must do the same as the eager mirror of that code over epochs that cross two grid updates."""
+    runs = []
+    for fused in (True, False):
+        g = load("poisson_2D_1C")
+        model, conds, pinn = build_pinn("poisson_2D_1C", g)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        reg = mp.PointwiseLosses(ignored_indexes=[1], lr=0.05)
+        tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=7, update_grid_every=3, calc_loss=reg)
+        tr.use_fused_step = fused
+        totals, lam = [], []
+        for e in range(1, 8):          # grid updates (and weight resets) at epochs 3 and 6
+            tr.current_epoch = e
+            tr._train_epoch()
+            totals.append(float(tr.total_loss))
+            lam.append(reg.models[0][0].weight.detach().numpy().reshape(-1)[:8].copy())
+        assert len(reg.optimizers) == 3
+        runs.append((np.array(totals), np.array(lam), model.jet_engine.flat.detach().numpy().copy()))
+    (t0, l0, w0), (t1, l1, w1) = runs
+    assert relerr(t0, t1) < 1e-5
+    assert np.abs(l0 - l1).max() < 1e-5
+    assert not np.allclose(l0[1], 1.0) and np.allclose(l0[2:], 1.0)      # trained on epoch 2, reset (for good) at 3
+    assert np.abs(w0 - w1).max() < 1e-5

@@ -252,7 +252,8 @@ class FusedStep:
         eng = trainer._engine
         if eng is None or eng.points_grad or trainer.num_batches < 1:
             return None
-        from .regularization import ConstantLosses, GradientLosses, NormalLosses, PointwiseLosses
+        from .regularization import (AdaptiveConditionsLosses, ConstantLosses, GradientLosses, NormalLosses,
+                                     PointwiseLosses)
         from .trainer.trainer import Trainer
         reg = None
         if trainer.calc_loss == Trainer.mean_calc_loss:
@@ -262,6 +263,8 @@ class FusedStep:
         elif type(trainer.calc_loss) in (ConstantLosses, GradientLosses, NormalLosses):
             reg = trainer.calc_loss
             mode = {ConstantLosses: "constant", GradientLosses: "gradient", NormalLosses: "normal"}[type(reg)]
+        elif type(trainer.calc_loss) is AdaptiveConditionsLosses and trainer.calc_loss.adaptive_cond is None:
+            reg, mode = trainer.calc_loss, "adaptive"
         elif type(trainer.calc_loss) is PointwiseLosses and trainer.calc_loss.optimizer_def is torch.optim.Adam \
                 and trainer.num_batches == 1 and not trainer.calc_loss.models:
             reg, mode = trainer.calc_loss, "pointwise"
@@ -319,6 +322,21 @@ class FusedStep:
             elif self.mode == "constant":  # total = sum_k lambda_k mean_n r^2     (reference regularization/constant.py)
                 self.lambdas = torch.tensor([float(v) for v in self.reg.lambdas], dtype=torch.float32, device=device)
                 self.weights = self.inv_counts * self.lambdas
+            elif self.mode == "adaptive":    # total = sum_k softmax(theta)_k mean_n r_kn^2  (reference adaptive.py:7-153)
+                from .regularization.adaptive import AdaptiveWeightSum
+                self.weights = torch.zeros(K, dtype=torch.float32, device=device)
+                aw = AdaptiveWeightSum(counts, self.reg.lr).to(device)     # theta_0 = log(N_k), as the reference
+                self.reg.adaptive_cond = aw
+                self.ad_theta = aw.train_weight.data                        # the module's parameter IS the buffer
+                self.ad_w = torch.softmax(self.ad_theta, dim=0)
+                aw.weight = self.ad_w
+                self.ad_gtheta = torch.zeros(K, dtype=torch.float32, device=device)
+                self.ad_g = torch.zeros(K, dtype=torch.float32, device=device)
+                self.ad_m = torch.zeros(K, dtype=torch.float32, device=device)
+                self.ad_v = torch.zeros(K, dtype=torch.float32, device=device)
+                self.ad_state = torch.zeros(4, dtype=torch.float32, device=device)
+                self.ad_state[0] = float(self.reg.lr)
+                self._ad_calls = 0
             elif self.mode == "pointwise":   # total = sum_k sum_n lambda_kn r_kn^2  (reference pointwise.py:84-100)
                 self.weights = torch.ones(K, dtype=torch.float32, device=device)
                 self._pw_allocate(device)
@@ -436,6 +454,17 @@ class FusedStep:
             self.wsums.zero_()
             if self._pw_live and self._pw_calls > 0:
                 self._pw_ascent()
+        if self.mode == "adaptive":
+            # theta <- Adam(lr, maximize=True, weight_decay=1e-6) on d total / d theta of the PREVIOUS evaluation
+            # (AdaptiveWeightSum.forward steps its optimizer before it uses the weights; nothing to step the first time)
+            if self._ad_calls > 0:
+                be = backend()
+                torch.mul(self.ad_gtheta, -1.0, out=self.ad_g)
+                self.ad_g.add_(self.ad_theta, alpha=1e-6)
+                be.adam_tick(self.ad_state, 0.9, 0.999)
+                be.adam_step_dev(self.ad_theta, self.ad_g, self.ad_m, self.ad_v, self.ad_state, 0.9, 0.999, 1e-8, 1.0)
+            torch.softmax(self.ad_theta, dim=0, out=self.ad_w)
+            torch.mul(self.ad_w, self.inv_counts, out=self.weights)     # seeds: 2 w_k r / N_k
         for u in self.units:
             if isinstance(u, BatchedGroup):
                 u.launch(self.weights, self.sums, eng.flat_grad, [self.k0[self.runners.index(m)] for m in u.members])
@@ -453,6 +482,10 @@ class FusedStep:
         torch.mul(self.sums, self.inv_counts, out=lv[:K])
         if self.mode == "pointwise":     # reported: unweighted means; optimised: the weighted sums
             torch.sum(self.wsums, dim=0, out=lv[K])
+            return
+        if self.mode == "adaptive":      # total = w . L ;  d total / d theta = w * (L - total)   (softmax Jacobian)
+            torch.dot(self.ad_w, lv[:K], out=lv[K])
+            torch.mul(self.ad_w, lv[:K] - lv[K], out=self.ad_gtheta)
             return
         if self.mode == "mean":
             torch.mul(torch.sum(self.sums), self.inv_total, out=lv[K])
@@ -522,6 +555,8 @@ class FusedStep:
         self._graphed("_g_compute", self._compute)
         if self.mode == "pointwise":
             self._pw_calls += 1
+        if self.mode == "adaptive":
+            self._ad_calls += 1
 
     def update(self, grad_scale: float = 1.0) -> bool:
         """Optimizer step on the device; False if the optimizer is not the fused Adam (caller steps it)."""

@@ -374,14 +374,17 @@ def test_reloading_weights_invalidates_packed_operands():
 
 
 # ------------------------------------------------------------------------------ regularizers on CUDA
-@pytest.mark.parametrize("kind", ["normal", "pointwise"])
+@pytest.mark.parametrize("kind", ["normal", "pointwise", "adaptive"])
 def test_regularizers_match_reference_on_cuda(kind):
-    """NormalLosses / PointwiseLosses over 3 steps vs the reference's own run (tests/golden), on the device."""
+    """NormalLosses / PointwiseLosses / AdaptiveConditionsLosses over 3 steps vs the reference's own run (tests/golden),
+    on the device, as loss policies of the fused step."""
     g = load("poisson_2D_1C")
     gr = np.load(os.path.join(os.path.dirname(__file__), "golden", f"poisson_{kind}_reg.npz"))
     model, conds, pinn = golden_pinn("poisson_2D_1C", g)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    reg = mp.NormalLosses(alpha=0.9) if kind == "normal" else mp.PointwiseLosses(ignored_indexes=[1], lr=0.01)
+    reg = {"normal": lambda: mp.NormalLosses(alpha=0.9),
+           "pointwise": lambda: mp.PointwiseLosses(ignored_indexes=[1], lr=0.01),
+           "adaptive": lambda: mp.AdaptiveConditionsLosses(lr=0.05)}[kind]()
     tr = mp.TrainerOneBatch(pinn, opt, None, num_epochs=3, update_grid_every=10**9, calc_loss=reg)
     assert tr.fused_step() is not None      # both are loss policies of the fused step (the third step is a graph replay)
     for e in range(3):
@@ -389,6 +392,8 @@ def test_regularizers_match_reference_on_cuda(kind):
         tr._train_epoch()
         if kind == "normal":
             assert relerr(reg.lambda_regularization.cpu().numpy(), gr["lambdas"][e]) < 5e-4
+        elif kind == "adaptive":
+            assert relerr(reg.adaptive_cond.weight.detach().cpu().numpy(), gr["lambdas"][e]) < 2e-5
         else:
             ms = reg.models[0]
             lam = np.concatenate([ms[0].weight.detach().cpu().numpy().reshape(-1)[:16],

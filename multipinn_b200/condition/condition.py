@@ -12,10 +12,54 @@ from __future__ import annotations
 import weakref
 from typing import Callable, List, Union
 
+import numpy as np
 import torch
 
 from .. import trace as _trace
 from ..jet import ResidualPlan, UnsupportedDerivative, use_plan
+
+
+def closure_fingerprint(fn, depth: int = 3) -> tuple:
+    """Numbers and small tensors a residual callable reads from its closure cells and module globals (recursing into
+    the plain functions it closes over).  A traced program has them baked in as constants; examples such as
+    ``examples/convection_1D_gradual_learning/problem.py:16-19`` change one through a ``nonlocal`` setter during
+    training (reference ``trainer/gradual_trainer.py:30-35``), which must re-trace the residual."""
+    items, seen = [], set()
+
+    def value(v):
+        if isinstance(v, (bool, int, float, complex, str)):
+            return v
+        if isinstance(v, torch.Tensor) and v.numel() <= 16:
+            return tuple(v.detach().reshape(-1).tolist())
+        if isinstance(v, np.ndarray) and v.size <= 16:
+            return tuple(v.reshape(-1).tolist())
+        if isinstance(v, (list, tuple)) and len(v) <= 16 and all(isinstance(e, (bool, int, float)) for e in v):
+            return tuple(v)
+        return None
+
+    def visit(f, d):
+        code = getattr(f, "__code__", None)
+        if code is None or id(f) in seen or d < 0:
+            return
+        seen.add(id(f))
+        for name, cell in zip(code.co_freevars, f.__closure__ or ()):
+            try:
+                v = cell.cell_contents
+            except ValueError:
+                continue
+            val = value(v)
+            if val is not None:
+                items.append((name, val))
+            elif callable(v):
+                visit(v, d - 1)
+        g = getattr(f, "__globals__", {})
+        for name in code.co_names:
+            val = value(g.get(name)) if name in g else None
+            if val is not None:
+                items.append(("global:" + name, val))
+
+    visit(fn, depth)
+    return tuple(items)
 
 
 class Condition:
@@ -29,6 +73,7 @@ class Condition:
         self.output_len = None
         self._plans = weakref.WeakKeyDictionary()
         self._programs = weakref.WeakKeyDictionary()   # model -> traced ResidualProgram, or None (eager path)
+        self._fingerprints = weakref.WeakKeyDictionary()   # model -> closure_fingerprint at trace time
         self.trace_note = None                         # why the last trace attempt fell back, for diagnostics
 
     # -- jet-order bookkeeping -------------------------------------------------------------
@@ -44,11 +89,16 @@ class Condition:
 
     # -- traced residual programs (fused train step) ------------------------------------------
     def program_for(self, model):
-        """The device program this condition's residual was traced into for ``model``, or None."""
+        """The device program this condition's residual was traced into for ``model``, or None.  Re-traced when a
+        constant the callable closes over has changed since (see ``closure_fingerprint``)."""
         try:
-            return self._programs.get(model)
+            prog = self._programs.get(model)
         except TypeError:
             return None
+        if model in self._programs and self._fingerprints.get(model) != closure_fingerprint(self.function):
+            self._trace(model, self._probe_point(model))
+            prog = self._programs.get(model)
+        return prog
 
     def _trace(self, model, probe: torch.Tensor) -> None:
         """Try to record the residual as a device program and check it against the eager residual at a few
@@ -60,6 +110,7 @@ class Condition:
             return
         try:
             self._programs[model] = None
+            self._fingerprints[model] = closure_fingerprint(self.function)
         except TypeError:
             return
         try:

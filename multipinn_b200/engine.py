@@ -211,6 +211,7 @@ class JetEngine:
         # opt-in: also produce dL/d(points) in the reverse pass, so that `points.grad` is populated like the
         # reference's backward() does (only its adversarial point generator reads it)
         self.points_grad = False
+        self._packed_version = -1
         self.flat: Optional[torch.Tensor] = None
         self.flat_grad: Optional[torch.Tensor] = None
         self.packed: Optional[torch.Tensor] = None
@@ -317,10 +318,21 @@ class JetEngine:
             self._tc_ok[order] = ok
         return ok
 
+    def _param_versions(self) -> int:
+        """Sum of the parameters' autograd version counters: grows with every in-place write torch knows about
+        (``reset_parameters()``, ``p.copy_()``, an optimizer step ...) -- not with writes through ``.data`` or with the
+        raw-pointer updates of this package's own Adam kernel, after which the operands are re-packed anyway."""
+        return sum(p._version for p in self._params)
+
     def _ensure_packed(self):
+        ver = self._param_versions()
+        if ver != self._packed_version and self.packed_valid and self.managed:
+            self.generation += 1            # written behind the trainer's back (e.g. MarchingTrainer.reset_weights)
+            self.packed_valid = False
         if not (self.packed_valid and self.managed):
             backend().pack_params(self.ops, self.flat.detach(), self.packed)
             self.packed_valid = True
+        self._packed_version = ver
 
     # ---------------------------------------------------------------- kernels
     def _engine_id(self) -> int:

@@ -54,6 +54,20 @@ class ConditionRunner:
         keys = {(bb.order, tuple(bb.lap) if bb.lap is not None else None) for bb in self.blocks}
         self.stacked = len(self.blocks) > 1 and len(keys) == 1
 
+    # -- a constant of the residual changed (closure_fingerprint): the re-traced program usually has the same shape
+    def _shape(self, prog):
+        return (len(prog.outputs), prog.data_width,
+                tuple((b.o, b.order, None if b.lap is None else tuple(b.lap), b.points is None) for b in prog.blocks))
+
+    def swap_program(self, prog) -> bool:
+        """Take over a re-traced program in place (buffers, batching and policy state stay); False if its shape differs."""
+        if self._shape(prog) != self._shape(self.prog):
+            return False
+        self.prog = prog
+        for b, bb in enumerate(self.blocks):
+            bb.points_prog = prog.points_program(b)
+        return True
+
     # -- batching: conditions whose single model call has the same jet order share ONE forward and ONE reverse
     #    launch over their concatenated points (fewer tail waves and launches); each keeps its own residual program,
     #    which runs on its slice of the shared jet block
@@ -541,6 +555,23 @@ class FusedStep:
         g.replay()
         self.graph_replays += 1
         CudaBackend.gpu_launches += self._launches[which]   # the replay runs the same kernels as a direct call
+
+    def refresh(self) -> bool:
+        """Follow residuals whose closed-over constants changed since they were traced (``Condition.program_for``
+        re-traces them): programs of the same shape are swapped in and the captured graph is dropped; False means the
+        step has to be rebuilt (or, when a residual no longer traces, abandoned for the eager path)."""
+        model, changed = self.engine.model, False
+        for r in self.runners:
+            p = r.cond.program_for(model)
+            if p is r.prog:
+                continue
+            if p is None or not r.swap_program(p):
+                return False
+            changed = True
+        if changed:
+            self._g_compute = None
+            self._calls["_g_compute"] = 0
+        return True
 
     # ------------------------------------------------------------------ the step
     def compute(self):

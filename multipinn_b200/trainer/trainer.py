@@ -216,9 +216,18 @@ class Trainer:
             return self._fused
         return None
 
+    def _current_fused_step(self):
+        """``fused_step()`` after following residual constants that changed since the trace (GradualTrainer's
+        ``param_setter``, reference trainer/gradual_trainer.py:30-35)."""
+        fs = self.fused_step()
+        if fs is not None and not fs.refresh():
+            self._fused = None
+            fs = self.fused_step()
+        return fs
+
     def _fused_batch(self, batch_index: int) -> bool:
         """One whole optimisation step on the fused path; False if this trainer is not eligible."""
-        fs = self.fused_step()
+        fs = self._current_fused_step()
         if fs is None:
             return False
         self.current_batch = batch_index
@@ -294,7 +303,7 @@ class TrainerMultiGPU(Trainer):
                 dist.broadcast(p.data, src=0)
 
     def _fused_dp_step(self) -> bool:
-        fs = self.fused_step()
+        fs = self._current_fused_step()
         if fs is None:
             return False
         self.pinn.select_batch(0 if self.sharded_points else self.rank)

@@ -371,6 +371,26 @@ def test_reloading_weights_invalidates_packed_operands():
     model.load_state_dict(sd0)
     with torch.no_grad():
         assert torch.equal(model(x), y0)
+    # in-place re-initialisation behind the trainer's back (MarchingTrainer.reset_weights, reference
+    # trainer/marching.py:35-40): noticed through the parameters' version counters, operands re-packed, and the next
+    # fused step (a graph replay by now) trains the NEW weights
+    for e in (2, 3, 4):
+        tr.current_epoch = e
+        tr._train_epoch()
+    torch.manual_seed(7)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Linear):
+            mod.reset_parameters()
+    with torch.no_grad():
+        y2 = model(x).clone()
+    ref = AR.MODELS["FNN"](2, 1, hidden_layers=[64] * 9).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in model.state_dict().items()})
+    assert relerr(y2.cpu().numpy(), ref(torch.tensor(g["pts0"]).double()).detach().numpy()) < 1e-5
+    before = model.jet_engine.flat.detach().clone()
+    tr.current_epoch = 5
+    tr._train_epoch()
+    step = (model.jet_engine.flat.detach() - before).abs().max()
+    assert 0 < float(step) < 2e-2          # one Adam step of size ~lr from the re-initialised weights, not a jump back
 
 
 # ------------------------------------------------------------------------------ regularizers on CUDA

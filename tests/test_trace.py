@@ -585,3 +585,88 @@ def test_masks_select_and_max_min_are_traced():
     c = mp.Condition(branching, mp.Hypercube([0, 0], [1, 1]))
     c.init_output_len(model)
     assert c.program_for(model) is None and "branches" in c.trace_note
+
+
+def test_changed_residual_constants_are_followed(oracle_backend):
+    """GradualTrainer (reference trainer/gradual_trainer.py:23-40) changes a problem parameter through a `nonlocal`
+    setter while training (examples/convection_1D_gradual_learning/problem.py:16-19).  The traced program has the old
+    value baked in: the closure fingerprint must trigger a re-trace, the fused step must take the new program over in
+    place, and the numbers must equal a trainer built from scratch with the new value."""
+    def problem(betta):
+        def inner(m, a):
+            (p,) = mp.unpack(m(a))
+            p_t, p_x = mp.unpack(mp.grad(p, a))
+            return [p_t + betta * p_x]
+
+        def setter(v):
+            nonlocal betta
+            betta = v
+        return inner, setter
+
+    geo = mp.Hypercube([0, 0], [1, 1])
+    pts = torch.rand((32, 2), generator=torch.Generator().manual_seed(3)).requires_grad_()
+
+    def trainer_for(fn, model):
+        cond = mp.Condition(fn, geo)
+        cond.generator = types.SimpleNamespace(n_points=32, generate=lambda c, m: pts)
+        pinn = mp.PINN(model, [cond])
+        pinn.update_data()
+        tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-3), None, num_epochs=5,
+                                update_grid_every=10**9)
+        return tr, cond
+
+    torch.manual_seed(0)
+    model = mp.FNN(2, 1, [16, 16])
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    fn, setter = problem(1.0)
+    tr, cond = trainer_for(fn, model)
+    fs = tr.fused_step()
+    assert fs is not None
+    tr.current_epoch = 1
+    tr._train_epoch()
+    prog0 = cond.program_for(model)
+    setter(7.5)                                   # what GradualTrainer.train does between epochs
+    tr.current_epoch = 2
+    tr._train_epoch()
+    assert tr.fused_step() is fs                  # same executor, new program
+    assert cond.program_for(model) is not prog0 and 7.5 in cond.program_for(model).consts
+    loss_after_change = float(tr.total_loss)
+    # reference run: identical first step with betta = 1, then a fresh trainer that has betta = 7.5 from the start
+    torch.manual_seed(0)
+    model2 = mp.FNN(2, 1, [16, 16])
+    model2.load_state_dict(state)
+    fn2, setter2 = problem(1.0)
+    tr2, _ = trainer_for(fn2, model2)
+    tr2.use_fused_step = False                    # eager path evaluates the Python callable every step
+    tr2.current_epoch = 1
+    tr2._train_epoch()
+    setter2(7.5)
+    tr2.current_epoch = 2
+    tr2._train_epoch()
+    assert relerr(loss_after_change, float(tr2.total_loss)) < 1e-5
+    assert np.abs(model.jet_engine.flat.detach().numpy() - model2.jet_engine.flat.detach().numpy()).max() < 1e-6
+
+
+def test_in_place_parameter_writes_are_noticed(oracle_backend):
+    """MarchingTrainer.reset_weights (reference trainer/marching.py:35-40) re-initialises the Linear layers in place
+    between stages.  The engine compares the parameters' version counters before every launch and re-packs its
+    operand images; derivative blocks computed with the old weights are not reused."""
+    torch.manual_seed(0)
+    model = mp.FNN(2, 1, [16, 16])
+    x = torch.rand(5, 2)
+    tr_like = model.jet_engine
+    tr_like.managed = True                        # as under a Trainer: operands are re-packed only when invalid
+    y0 = model(x).detach().clone()
+    gen0 = tr_like.generation
+    calls = [c for c in oracle_backend.calls if c[0] == "pack"]
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Linear):
+            mod.reset_parameters()
+    y1 = model(x).detach()
+    assert tr_like.generation > gen0
+    assert not torch.allclose(y0, y1)
+    ref = torch.nn.Sequential()
+    from oracle import autograd_ref as AR
+    r = AR.MODELS["FNN"](2, 1, hidden_layers=[16, 16]).double()
+    r.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    assert relerr(y1.numpy(), r(x.double()).detach().numpy()) < 1e-6

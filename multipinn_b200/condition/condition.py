@@ -95,10 +95,16 @@ class Condition:
             prog = self._programs.get(model)
         except TypeError:
             return None
-        if model in self._programs and self._fingerprints.get(model) != closure_fingerprint(self.function):
+        if model in self._programs and not self._same_residual(model):
             self._trace(model, self._probe_point(model))
             prog = self._programs.get(model)
         return prog
+
+    def _same_residual(self, model) -> bool:
+        """The callable traced for ``model`` is still this condition's ``function`` (MarchingTrainer stages replace
+        it: examples/convection_1D_marching/problem.py:53-54) and closes over the same constants."""
+        fn, fp = self._fingerprints.get(model, (None, None))
+        return fn is self.function and fp == closure_fingerprint(self.function)
 
     def _trace(self, model, probe: torch.Tensor) -> None:
         """Try to record the residual as a device program and check it against the eager residual at a few
@@ -110,7 +116,7 @@ class Condition:
             return
         try:
             self._programs[model] = None
-            self._fingerprints[model] = closure_fingerprint(self.function)
+            self._fingerprints[model] = (self.function, closure_fingerprint(self.function))
         except TypeError:
             return
         try:

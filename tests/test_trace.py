@@ -670,3 +670,45 @@ def test_in_place_parameter_writes_are_noticed(oracle_backend):
     r = AR.MODELS["FNN"](2, 1, hidden_layers=[16, 16]).double()
     r.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
     assert relerr(y1.numpy(), r(x.double()).detach().numpy()) < 1e-6
+
+
+def test_replaced_residual_function_is_retraced(oracle_backend):
+    """MarchingTrainer stages replace a condition's function, the new one calling the PREVIOUS stage's model as well
+    (examples/convection_1D_marching/problem.py:39-56): the cached program must not survive; a residual that calls two
+    models does not trace and the trainer continues on the eager path."""
+    import copy
+    torch.manual_seed(0)
+    model = mp.FNN(2, 1, [16, 16])
+    geo = mp.Hypercube([0, 0], [1, 1])
+
+    def ic(m, a):
+        (u,) = mp.unpack(m(a))
+        x, y = mp.unpack(a)
+        return [u - torch.sin(y)]
+
+    cond = mp.Condition(ic, geo)
+    pts = torch.rand((16, 2), generator=torch.Generator().manual_seed(3)).requires_grad_()
+    cond.generator = types.SimpleNamespace(n_points=16, generate=lambda c, m: pts)
+    pinn = mp.PINN(model, [cond])
+    pinn.update_data()
+    tr = mp.TrainerOneBatch(pinn, torch.optim.Adam(model.parameters(), lr=1e-3), None, num_epochs=3,
+                            update_grid_every=10**9)
+    tr.current_epoch = 1
+    tr._train_epoch()
+    assert tr.fused_step() is not None
+    previous = copy.deepcopy(model)
+
+    def ic_new(m, a):
+        (u,) = mp.unpack(m(a))
+        (u_prev,) = mp.unpack(previous(a))
+        return [u - u_prev]
+
+    cond.function = ic_new
+    tr.current_epoch = 2
+    tr._train_epoch()
+    assert tr.fused_step() is None and "two different models" in cond.trace_note
+    with torch.no_grad():
+        want = float(((model(pts) - previous(pts)) ** 2).mean())
+    tr.current_epoch = 3
+    tr._train_epoch()
+    assert abs(float(tr.total_loss) - want) / want < 1e-5

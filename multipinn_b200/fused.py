@@ -277,7 +277,8 @@ class FusedStep:
         elif type(trainer.calc_loss) in (ConstantLosses, GradientLosses, NormalLosses):
             reg = trainer.calc_loss
             mode = {ConstantLosses: "constant", GradientLosses: "gradient", NormalLosses: "normal"}[type(reg)]
-        elif type(trainer.calc_loss) is AdaptiveConditionsLosses and trainer.calc_loss.adaptive_cond is None:
+        elif type(trainer.calc_loss) is AdaptiveConditionsLosses and (
+                trainer.calc_loss.adaptive_cond is None or hasattr(trainer.calc_loss.adaptive_cond, "_fused_state")):
             reg, mode = trainer.calc_loss, "adaptive"
         elif type(trainer.calc_loss) is PointwiseLosses and trainer.calc_loss.optimizer_def is torch.optim.Adam \
                 and trainer.num_batches == 1 and not trainer.calc_loss.models:
@@ -339,18 +340,23 @@ class FusedStep:
             elif self.mode == "adaptive":    # total = sum_k softmax(theta)_k mean_n r_kn^2  (reference adaptive.py:7-153)
                 from .regularization.adaptive import AdaptiveWeightSum
                 self.weights = torch.zeros(K, dtype=torch.float32, device=device)
-                aw = AdaptiveWeightSum(counts, self.reg.lr).to(device)     # theta_0 = log(N_k), as the reference
-                self.reg.adaptive_cond = aw
+                aw = self.reg.adaptive_cond
+                st = getattr(aw, "_fused_state", None)
+                if st is None or st["m"].numel() != K or st["m"].device != device:
+                    aw = AdaptiveWeightSum(counts, self.reg.lr).to(device)  # theta_0 = log(N_k), as the reference
+                    st = {"gtheta": torch.zeros(K, dtype=torch.float32, device=device),
+                          "m": torch.zeros(K, dtype=torch.float32, device=device),
+                          "v": torch.zeros(K, dtype=torch.float32, device=device),
+                          "state": torch.zeros(4, dtype=torch.float32, device=device), "calls": 0}
+                    st["state"][0] = float(self.reg.lr)
+                    aw._fused_state = st      # lives with the policy object: survives a rebuild of this executor
+                    self.reg.adaptive_cond = aw
                 self.ad_theta = aw.train_weight.data                        # the module's parameter IS the buffer
                 self.ad_w = torch.softmax(self.ad_theta, dim=0)
                 aw.weight = self.ad_w
-                self.ad_gtheta = torch.zeros(K, dtype=torch.float32, device=device)
+                self.ad_gtheta, self.ad_m, self.ad_v, self.ad_state = st["gtheta"], st["m"], st["v"], st["state"]
                 self.ad_g = torch.zeros(K, dtype=torch.float32, device=device)
-                self.ad_m = torch.zeros(K, dtype=torch.float32, device=device)
-                self.ad_v = torch.zeros(K, dtype=torch.float32, device=device)
-                self.ad_state = torch.zeros(4, dtype=torch.float32, device=device)
-                self.ad_state[0] = float(self.reg.lr)
-                self._ad_calls = 0
+                self._ad_st = st
             elif self.mode == "pointwise":   # total = sum_k sum_n lambda_kn r_kn^2  (reference pointwise.py:84-100)
                 self.weights = torch.ones(K, dtype=torch.float32, device=device)
                 self._pw_allocate(device)
@@ -471,7 +477,7 @@ class FusedStep:
         if self.mode == "adaptive":
             # theta <- Adam(lr, maximize=True, weight_decay=1e-6) on d total / d theta of the PREVIOUS evaluation
             # (AdaptiveWeightSum.forward steps its optimizer before it uses the weights; nothing to step the first time)
-            if self._ad_calls > 0:
+            if self._ad_st["calls"] > 0:
                 be = backend()
                 torch.mul(self.ad_gtheta, -1.0, out=self.ad_g)
                 self.ad_g.add_(self.ad_theta, alpha=1e-6)
@@ -587,7 +593,7 @@ class FusedStep:
         if self.mode == "pointwise":
             self._pw_calls += 1
         if self.mode == "adaptive":
-            self._ad_calls += 1
+            self._ad_st["calls"] += 1
 
     def update(self, grad_scale: float = 1.0) -> bool:
         """Optimizer step on the device; False if the optimizer is not the fused Adam (caller steps it)."""

@@ -221,8 +221,13 @@ class Trainer:
         ``param_setter``, reference trainer/gradual_trainer.py:30-35)."""
         fs = self.fused_step()
         if fs is not None and not fs.refresh():
+            was_pointwise = fs.mode == "pointwise"
             self._fused = None
             fs = self.fused_step()
+            if fs is None and was_pointwise:
+                raise RuntimeError(
+                    "a residual changed shape (or stopped tracing) while the per-point weights of PointwiseLosses "
+                    "live on the fused step; construct the trainer with use_fused_step = False for this problem")
         return fs
 
     def _fused_batch(self, batch_index: int) -> bool:

@@ -17,7 +17,17 @@
 
 namespace mpinn {
 
-constexpr int kThreads = 256;
+// Threads per CTA and output features per thread-chunk.  256 / 8 is the shipped configuration; the diagnostic build
+// -DMPINN_FFMA_THREADS=512 -DMPINN_FFMA_CH=4 doubles the resident warps (same shared memory) for 128-wide layers.
+#ifndef MPINN_FFMA_THREADS
+#define MPINN_FFMA_THREADS 256
+#endif
+#ifndef MPINN_FFMA_CH
+#define MPINN_FFMA_CH 8
+#endif
+constexpr int kThreads = MPINN_FFMA_THREADS;
+constexpr int kCh = MPINN_FFMA_CH;      // 4 or 8
+static_assert(kCh == 4 || kCh == 8, "chunk width");
 
 // ---------------------------------------------------------------------------------------------
 // helpers
@@ -29,26 +39,30 @@ __device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict
   for (int i = threadIdx.x; i < n_floats / 4; i += kThreads) d4[i] = __ldg(s4 + i);
 }
 
-// acc[f][j] += sum_k Ws[k*ldw + 8*chunk + f] * hin[(j*W + k)*TPP + p]
+// acc[f][j] += sum_k Ws[k*ldw + kCh*chunk + f] * hin[(j*W + k)*TPP + p]
 template <int J, int TPP>
 __device__ __forceinline__ void gemm_chunk(const float* __restrict__ hin, const float* __restrict__ Ws,
                                            int kdim, int ldw, int chunk, int W, int p,
-                                           float (&acc)[8][J]) {
+                                           float (&acc)[kCh][J]) {
 #pragma unroll
-  for (int f = 0; f < 8; ++f)
+  for (int f = 0; f < kCh; ++f)
 #pragma unroll
     for (int j = 0; j < J; ++j) acc[f][j] = 0.0f;
-  const float* wrow = Ws + 8 * chunk;
+  const float* wrow = Ws + kCh * chunk;
 #pragma unroll 2
   for (int k = 0; k < kdim; ++k) {
+    float w[kCh];
     const float4 w0 = *reinterpret_cast<const float4*>(wrow + k * ldw);
-    const float4 w1 = *reinterpret_cast<const float4*>(wrow + k * ldw + 4);
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+    if (kCh == 8) {
+      const float4 w1 = *reinterpret_cast<const float4*>(wrow + k * ldw + 4);
+      w[kCh - 4] = w1.x; w[kCh - 3] = w1.y; w[kCh - 2] = w1.z; w[kCh - 1] = w1.w;
+    }
     float h[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) h[j] = hin[(j * W + k) * TPP + p];
 #pragma unroll
-    for (int f = 0; f < 8; ++f)
+    for (int f = 0; f < kCh; ++f)
 #pragma unroll
       for (int j = 0; j < J; ++j) acc[f][j] = fmaf(w[f], h[j], acc[f][j]);
   }
@@ -149,12 +163,12 @@ jet_fwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
       const float* hskip = (op.flags & MPINN_FLAG_ADD_SKIP) ? bufs[skip] : nullptr;
       float* hout = bufs[nxt];
       const bool do_stash = (stash != nullptr) && (op.stash_plane >= 0);
-      for (int c = g; c < op.outp / 8; c += G) {
-        float acc[8][J];
+      for (int c = g; c < op.outp / kCh; c += G) {
+        float acc[kCh][J];
         gemm_chunk<J, TPP>(hin, Ws, op.in_dim, op.outp, c, W, p, acc);
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-          const int fo = 8 * c + f;
+        for (int f = 0; f < kCh; ++f) {
+          const int fo = kCh * c + f;
           if (fo < op.out_dim) {
             float z[J];
 #pragma unroll
@@ -386,12 +400,12 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
 
       // (4) grad wrt this op's input: C[j][i][p] = sum_o W[o][i] zbar[j][o][p] (+ skip branch)
       if (need_dinput) {
-        for (int c = g; c < op.inp / 8; c += G) {
-          float acc[8][J];
+        for (int c = g; c < op.inp / kCh; c += G) {
+          float acc[kCh][J];
           gemm_chunk<J, TPP>(bufG, Ws, op.out_dim, op.inp, c, W, p, acc);
 #pragma unroll
-          for (int f = 0; f < 8; ++f) {
-            const int fi = 8 * c + f;
+          for (int f = 0; f < kCh; ++f) {
+            const int fi = kCh * c + f;
             if (fi < op.in_dim) {
 #pragma unroll
               for (int j = 0; j < J; ++j) {

@@ -292,6 +292,45 @@ def long_run_case(mp, steps=1000):
     return out
 
 
+def long_run_family_case(mp, case, steps=300):
+    """`steps` free-running TrainerOneBatch steps of the UNMODIFIED reference from a golden case's weights / points
+    (Adam 1e-3, ExponentialLR 0.9999) in fp64 and fp32: the total-loss curves and the fp64 weights after 100 steps.
+    Pins the oracle port over a long run for the residual-block and Fourier-feature families (the 1 000-step poisson
+    fixture does it for the plain FNN)."""
+    name, modname, factory, model_name, kwargs, _ = case
+    g = np.load(os.path.join(HERE, name + ".npz"))
+    out = {}
+    for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        mod = importlib.import_module(modname)
+        conds, din, dout = getattr(mod, factory)()
+        model = getattr(mp.neural_network, model_name)(input_dim=din, output_dim=dout, **kwargs).to(dtype)
+        model.load_state_dict({k: torch.tensor(g["w::" + k]).to(dtype) for k in g["state_keys"]})
+        for i, c in enumerate(conds):
+            p = torch.tensor(g[f"pts{i}"], dtype=dtype).requires_grad_()
+            c.generator = _FixedGenerator(p)
+            c.points, c.batch_size = p, len(p)
+        if dtype == torch.float32:
+            pinn = mp.PINN(model=model, conditions=conds)
+        else:
+            pinn = mp.PINN.__new__(mp.PINN)
+            pinn.model, pinn.conditions = model, conds
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+        tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=steps, update_grid_every=10**9, calc_loss="mean",
+                                callbacks_organizer=mp.CallbacksOrganizer([]))
+        curve = []
+        for e in range(steps):
+            tr.current_epoch = e + 1
+            tr._train_epoch()
+            sched.step()
+            curve.append(float(tr.total_loss))
+            if dtype == torch.float64 and e + 1 == 100:
+                out["params_f64_after100"] = np.concatenate(
+                    [p.detach().numpy().reshape(-1) for p in model.parameters()])
+        out[f"loss_{tag}"] = np.array(curve)
+    return out
+
+
 def activation_kats(mp):
     """The reference's own known-answer vectors (tests/neural_network/test_activation_function.py:8-59)."""
     from multipinn.neural_network.activation_function import fused_gelu, fused_sin
@@ -319,6 +358,12 @@ def main():
         d = np.abs(out["loss_f32"] - out["loss_f64"]) / out["loss_f64"]
         print("poisson_1k: loss", out["loss_f64"][[0, 99, 999]], "fp32-vs-fp64 rel dev at 100/500/1000:",
               d[99], d[499], d[999], "max", d.max())
+    for case in CASES:
+        if case[0] in ("navier_stokes_2D", "navier_stokes_3D") and (not only or case[0] + "_300" in only):
+            out = long_run_family_case(mp, case)
+            np.savez_compressed(os.path.join(HERE, case[0] + "_300.npz"), **out)
+            d = np.abs(out["loss_f32"] - out["loss_f64"]) / out["loss_f64"]
+            print(case[0] + "_300: loss", out["loss_f64"][[0, 99, 299]], "fp32-vs-fp64 rel dev max", d.max())
     for kind in ("gradient", "normal", "pointwise", "adaptive", "adaptive_points"):
         if not only or f"{kind}_reg" in only:
             out = gradient_reg_case(mp, kind)

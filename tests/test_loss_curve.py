@@ -148,3 +148,96 @@ def test_free_running_1000_steps_stay_inside_reference_envelope():
     assert inside >= 100
     assert bool((dev <= np.maximum(1e-4, 10.0 * env)).all()), int(np.argmax(dev > np.maximum(1e-4, 10.0 * env)))
     assert np.isfinite(curve).all() and curve[-1] < 0.01 * curve[0]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the other two model families: residual blocks (navier_stokes_2D) and Fourier features (navier_stokes_3D), 300 steps
+FAMILY_300 = {name: np.load(os.path.join(GOLD, name + "_300.npz")) for name in ("navier_stokes_2D", "navier_stokes_3D")}
+
+
+def _port_of(name, dtype, device):
+    from tests.test_oracle_golden import GOLD_KW
+    g = load(name)
+    ns = types.SimpleNamespace(grad=AR.grad, unpack=AR.unpack, Symbols=None)
+    fn, kind, _ = problems.CONFIGS[name]
+    spec, din, dout = fn(ns)
+    m = AR.MODELS[kind](din, dout, **GOLD_KW[name]).to(dtype).to(device)
+    m.load_state_dict({k: torch.tensor(g["w::" + k]).to(dtype) for k in g["state_keys"]})
+    pts = [torch.tensor(g[f"pts{i}"], dtype=dtype, device=device).requires_grad_() for i in range(len(spec))]
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    return m, [f for f, _ in spec], pts, opt, sched
+
+
+@pytest.mark.parametrize("name", sorted(FAMILY_300))
+def test_port_fp64_follows_unmodified_reference_curve_other_families(name):
+    """120 free-running fp64 steps of the oracle port == the unmodified reference's fp64 run for the residual-block
+    and Fourier-feature networks (loss every step, weights after 100 steps)."""
+    K = FAMILY_300[name]
+    m, fns, pts, opt, sched = _port_of(name, torch.float64, "cpu")
+    curve = []
+    for e in range(120):
+        total, _ = AR.train_step(m, opt, fns, pts)
+        sched.step()
+        curve.append(float(total))
+        if e + 1 == 100:
+            flat = np.concatenate([p.detach().numpy().reshape(-1) for p in m.parameters()])
+            assert np.abs(flat - K["params_f64_after100"]).max() < 1e-8
+    assert relerr(np.array(curve), K["loss_f64"][:120]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FAMILY_300))
+def test_teacher_forced_300_steps_other_families(name):
+    """Teacher-forced parity (see the poisson test above) for the ResNet and the Fourier-feature network: at each of 300
+    steps the reference algorithm's fp32 weights and Adam state are loaded, one fused step is taken, the loss is compared
+    with the fp64 truth at those weights and the updated weights with the reference's.  Same gates: 1e-4 everywhere,
+    max(1e-5, 2 * 3e-6 * cancellation) per step, weights within 5e-6."""
+    import multipinn_b200 as mp
+    from multipinn_b200 import engine, jet
+    from tests.test_gpu_fused import golden_pinn
+    engine._set_backend_for_tests(None)
+    jet.clear_blocks()
+    g = load(name)
+    model, conds, pinn = golden_pinn(name, g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    tr = mp.TrainerOneBatch(pinn, opt, sched, num_epochs=300, update_grid_every=10**9)
+    assert tr.fused_step() is not None and tr._flat_adam is not None
+    rm, fns, pts, ropt, rsched = _port_of(name, torch.float32, "cuda")
+    tm, _, tpts, _, _ = _port_of(name, torch.float64, "cuda")
+    eng, fa = model.jet_engine, tr._flat_adam
+    rparams, tparams = list(rm.parameters()), list(tm.parameters())
+    # the mirror packs parameters in the order the reference iterates them (frozen Fourier matrix included)
+    assert sum(p.numel() for p in rparams) == eng.flat.numel()
+    dls, dws, truths = [], [], []
+    for step in range(300):
+        with torch.no_grad():
+            eng.flat.detach().copy_(torch.cat([p.detach().reshape(-1) for p in rparams]))
+            eng.invalidate()
+            for tp, rp in zip(tparams, rparams):
+                tp.copy_(rp.double())
+            if step:
+                zeros = lambda p: torch.zeros(p.numel(), device="cuda")      # noqa: E731 -- frozen B has no Adam state
+                fa.load_state(torch.cat([ropt.state[p]["exp_avg"].reshape(-1) if p in ropt.state else zeros(p)
+                                         for p in rparams]),
+                              torch.cat([ropt.state[p]["exp_avg_sq"].reshape(-1) if p in ropt.state else zeros(p)
+                                         for p in rparams]), step)
+        opt.param_groups[0]["lr"] = ropt.param_groups[0]["lr"]
+        truth = float(AR.mean_loss(tm, fns, tpts)[0].detach())
+        AR.train_step(rm, ropt, fns, pts)
+        rsched.step()
+        tr.current_epoch = step + 1
+        tr._train_epoch()
+        truths.append(truth)
+        dls.append(abs(float(tr.total_loss) - truth) / abs(truth))
+        with torch.no_grad():
+            dws.append(float((eng.flat.detach() - torch.cat([p.detach().reshape(-1) for p in rparams])).abs().max()))
+    dls, dws, truths = np.array(dls), np.array(dws), np.array(truths)
+    cancel = np.sqrt(truths[0] / truths)
+    print(f"{name}: teacher-forced 300 steps: loss rel err vs fp64 truth worst {dls.max():.2e} (step {dls.argmax()}), "
+          f"median {np.median(dls):.2e}; updated-weight abs diff worst {dws.max():.2e}")
+    assert dls.max() < 1e-4
+    bound = np.maximum(1e-5, 2.0 * 3e-6 * cancel)
+    assert bool((dls <= bound).all()), (int(np.argmax(dls > bound)), float(dls.max()))
+    assert dws.max() < 5e-6

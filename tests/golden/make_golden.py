@@ -359,7 +359,8 @@ def main():
         print("poisson_1k: loss", out["loss_f64"][[0, 99, 999]], "fp32-vs-fp64 rel dev at 100/500/1000:",
               d[99], d[499], d[999], "max", d.max())
     for case in CASES:
-        if case[0] in ("navier_stokes_2D", "navier_stokes_3D") and (not only or case[0] + "_300" in only):
+        if case[0] in ("navier_stokes_2D", "navier_stokes_3D", "burgers_1D", "allen_cahn_2D_1C") and \
+                (not only or case[0] + "_300" in only):
             out = long_run_family_case(mp, case)
             np.savez_compressed(os.path.join(HERE, case[0] + "_300.npz"), **out)
             d = np.abs(out["loss_f32"] - out["loss_f64"]) / out["loss_f64"]

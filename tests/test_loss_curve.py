@@ -152,7 +152,7 @@ def test_free_running_1000_steps_stay_inside_reference_envelope():
 
 # ------------------------------------------------------------------------------------------------------------------
 # the other two model families: residual blocks (navier_stokes_2D) and Fourier features (navier_stokes_3D), 300 steps
-FAMILY_300 = {name: np.load(os.path.join(GOLD, name + "_300.npz")) for name in ("navier_stokes_2D", "navier_stokes_3D")}
+FAMILY_300 = {name: np.load(os.path.join(GOLD, name + "_300.npz")) for name in ("navier_stokes_2D", "navier_stokes_3D", "burgers_1D", "allen_cahn_2D_1C")}
 
 
 def _port_of(name, dtype, device):

@@ -252,13 +252,14 @@ class FusedStep:
                       for u in self.units]
         self.use_graphs = use_graphs
         self._g_compute: Optional[torch.cuda.CUDAGraph] = None
+        self._g_compute_acc: Optional[torch.cuda.CUDAGraph] = None     # same, adding to the gradient (batches > 0)
         self._g_update: Optional[torch.cuda.CUDAGraph] = None
-        self._calls = {"_g_compute": 0, "_g_update": 0}
+        self._calls = {"_g_compute": 0, "_g_compute_acc": 0, "_g_update": 0}
         self._dev = None
         self._lr_on_device = None
         self._scale = 1.0
         self.graph_replays = 0
-        self._launches = {"_g_compute": 0, "_g_update": 0}   # kernels one direct run of each part launches
+        self._launches = {"_g_compute": 0, "_g_compute_acc": 0, "_g_update": 0}   # kernels one direct run of each part launches
 
     @staticmethod
     def build(trainer) -> Optional["FusedStep"]:
@@ -266,6 +267,7 @@ class FusedStep:
         eng = trainer._engine
         if eng is None or eng.points_grad or trainer.num_batches < 1:
             return None
+        multi = trainer.num_batches > 1 and not hasattr(trainer, "rank")     # (TrainerMultiGPU: one batch per rank)
         from .regularization import (AdaptiveConditionsLosses, ConstantLosses, GradientLosses, NormalLosses,
                                      PointwiseLosses)
         from .trainer.trainer import Trainer
@@ -285,6 +287,8 @@ class FusedStep:
             reg, mode = trainer.calc_loss, "pointwise"
         else:
             return None
+        if multi and mode not in ("mean", "legacy", "constant"):
+            return None        # per-condition gradient policies and the weight-training ones: one batch only
         progs = []
         for c in trainer.pinn.conditions:
             p = c.program_for(trainer.pinn.model) if hasattr(c, "program_for") else None
@@ -321,8 +325,8 @@ class FusedStep:
                 changed |= u.bind(int(u.cond.batch_points.shape[0]), device)
         if changed:
             self._dev = device
-            self._g_compute = self._g_update = None
-            self._calls = {"_g_compute": 0, "_g_update": 0}
+            self._g_compute = self._g_compute_acc = self._g_update = None
+            self._calls = {"_g_compute": 0, "_g_compute_acc": 0, "_g_update": 0}
             eng.attach_grads()
             K = self.K
             counts = []
@@ -464,9 +468,10 @@ class FusedStep:
         be.adam_tick(self.pw_state, 0.9, 0.999)
         be.adam_step_dev(self.pw_lam, self.pw_g, self.pw_m, self.pw_v, self.pw_state, 0.9, 0.999, 1e-8, -1.0)
 
-    def _compute(self):
+    def _compute(self, accumulate: bool = False):
         eng = self.engine
-        eng.flat_grad.zero_()
+        if not accumulate:          # later batches of an epoch add to the gradient of the earlier ones
+            eng.flat_grad.zero_()
         self.sums.zero_()
         if self.per_condition:
             self.G.zero_()
@@ -575,13 +580,14 @@ class FusedStep:
                 return False
             changed = True
         if changed:
-            self._g_compute = None
-            self._calls["_g_compute"] = 0
+            self._g_compute = self._g_compute_acc = None
+            self._calls["_g_compute"] = self._calls["_g_compute_acc"] = 0
         return True
 
     # ------------------------------------------------------------------ the step
-    def compute(self):
-        """Gradient of the total loss into ``engine.flat_grad`` and the losses into the comm tail."""
+    def compute(self, accumulate: bool = False):
+        """Gradient of the total loss into ``engine.flat_grad`` (added to it with ``accumulate``: the second and later
+        batches of an epoch, reference trainer.py:119-153) and the losses into the comm tail."""
         conds = [r.cond for r in self.runners]
         self._bind(conds[0].batch_points.device)
         for r in self.runners:
@@ -589,7 +595,12 @@ class FusedStep:
         self.engine._ensure_packed()
         if self.mode == "pointwise":
             self._pw_sync_policy()
-        self._graphed("_g_compute", self._compute)
+        if accumulate:
+            if self.mode not in ("mean", "legacy", "constant"):
+                raise RuntimeError("gradient accumulation over batches is fused for the mean / legacy / constant policies")
+            self._graphed("_g_compute_acc", lambda: self._compute(True))
+        else:
+            self._graphed("_g_compute", self._compute)
         if self.mode == "pointwise":
             self._pw_calls += 1
         if self.mode == "adaptive":

@@ -243,8 +243,27 @@ class Trainer:
         self.total_loss, self.epoch_loss_detailed = fs.losses()
         return True
 
+    def _fused_batches(self) -> bool:
+        """An epoch of ``num_batches`` batches on the fused path: the gradient accumulates over the batches (the first
+        compute overwrites it, the others add), then ONE optimizer step (reference trainer.py:119-153)."""
+        fs = self._current_fused_step()
+        if fs is None:
+            return False
+        for self.current_batch in range(self.num_batches):
+            self.pinn.select_batch(self.current_batch)
+            fs.compute(accumulate=self.current_batch > 0)
+            total, losses = fs.losses()
+            self._accumulate(total, losses)
+        if not fs.update():
+            self._optimizer_step()
+        self.epoch_loss_detailed = self.epoch_loss_detailed * self.inum_batches
+        self.total_loss = self.total_loss * self.inum_batches
+        return True
+
     def _train_batches(self):
         if self.num_batches == 1 and self._fused_batch(0):
+            return
+        if self.num_batches > 1 and self._fused_batches():
             return
         self._zero_grad()  # outside the loop: gradients accumulate over the batches
         for self.current_batch in range(self.num_batches):

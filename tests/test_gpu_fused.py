@@ -740,3 +740,29 @@ def test_residual_kernel_per_point_loss_weights(cuda_backend):
         assert relerr(sums.cpu().numpy(), rs) < 5e-6, n
         assert relerr(wsums.cpu().numpy(), (lam.cpu().numpy().astype(np.float64) * rv ** 2).sum(axis=1)) < 5e-6, n
         assert relerr(dout.cpu().numpy(), rd[0]) < 5e-6, n
+
+
+@pytest.mark.gpu
+def test_multi_batch_epochs_on_cuda_graphs():
+    """Trainer(num_batches=2): two captured compute graphs (overwrite / accumulate) + one update graph per epoch, against
+    the eager jet path over 5 epochs."""
+    runs = []
+    for fused in (True, False):
+        g = load("poisson_2D_1C")
+        model, conds, pinn = golden_pinn("poisson_2D_1C", g)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        tr = mp.Trainer(pinn, opt, None, num_epochs=5, num_batches=2, update_grid_every=10**9)
+        tr.use_fused_step = fused
+        hist = []
+        for e in range(1, 6):
+            tr.current_epoch = e
+            tr._train_epoch()
+            hist.append(float(tr.total_loss))
+        if fused:
+            fs = tr.fused_step()
+            assert fs is not None and fs._g_compute is not None and fs._g_compute_acc is not None
+            assert fs.graph_replays >= 6
+        runs.append((np.array(hist), model.jet_engine.flat.detach().cpu().numpy().copy()))
+    (h0, w0), (h1, w1) = runs
+    assert relerr(h0, h1) < 2e-5
+    assert np.abs(w0 - w1).max() < 1e-5

@@ -712,3 +712,34 @@ def test_replaced_residual_function_is_retraced(oracle_backend):
     tr.current_epoch = 3
     tr._train_epoch()
     assert abs(float(tr.total_loss) - want) / want < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["mean", "legacy"])
+def test_multi_batch_epochs_accumulate_on_the_fused_step(mode, oracle_backend):
+    """`Trainer(num_batches=3)` (examples/navier_stokes_2D_obstacle/run_train.py:86): the gradient accumulates over the
+    batches and ONE optimizer step follows (reference trainer.py:119-153).  Fused path vs the eager jet path over 3
+    epochs: losses and weights."""
+    runs = []
+    for fused in (True, False):
+        g = load("poisson_2D_1C")
+        model, conds, pinn = build_pinn("poisson_2D_1C", g)
+        n_pts = [len(c.points) for c in conds]
+        assert all(n % 2 == 0 for n in n_pts)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        tr = mp.Trainer(pinn, opt, None, num_epochs=3, num_batches=2, update_grid_every=10**9, calc_loss=mode)
+        tr.use_fused_step = fused
+        hist = []
+        for e in range(1, 4):
+            tr.current_epoch = e
+            oracle_backend.calls.clear()
+            tr._train_epoch()
+            hist.append((float(tr.total_loss), tr.epoch_loss_detailed.numpy().copy()))
+            n_adam = sum(1 for c in oracle_backend.calls if c[0] in ("adam", "adam_dev"))
+            assert n_adam == 1                                   # one optimizer step per epoch, not per batch
+        if fused:
+            assert tr.fused_step() is not None
+        runs.append((hist, model.jet_engine.flat.detach().numpy().copy()))
+    (h0, w0), (h1, w1) = runs
+    for (t0, d0), (t1, d1) in zip(h0, h1):
+        assert relerr(t0, t1) < 1e-5 and relerr(d0, d1) < 1e-5
+    assert np.abs(w0 - w1).max() < 5e-6

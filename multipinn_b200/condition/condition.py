@@ -30,6 +30,8 @@ def closure_fingerprint(fn, depth: int = 3) -> tuple:
         if isinstance(v, (bool, int, float, complex, str)):
             return v
         if isinstance(v, torch.Tensor) and v.numel() <= 16:
+            if v.is_cuda:       # reading it back would synchronise the device at every step: identity + version instead
+                return ("cuda-tensor", id(v), v._version)
             return tuple(v.detach().reshape(-1).tolist())
         if isinstance(v, np.ndarray) and v.size <= 16:
             return tuple(v.reshape(-1).tolist())
@@ -138,7 +140,8 @@ class Condition:
         low = torch.as_tensor(self.geometry.bbox[0], dtype=torch.float32, device=probe.device)
         high = torch.as_tensor(self.geometry.bbox[1], dtype=torch.float32, device=probe.device)
         gen = torch.Generator(device="cpu").manual_seed(1234)
-        u = torch.rand((n, low.numel()), generator=gen, dtype=torch.float32).to(probe.device)
+        # (device named explicitly: the reference's run scripts set torch.set_default_device("cuda"), utils/device.py:47)
+        u = torch.rand((n, low.numel()), generator=gen, dtype=torch.float32, device="cpu").to(probe.device)
         return (low + (high - low) * u).contiguous()
 
     def _check_program(self, model, prog, probe: torch.Tensor, n: int = 8) -> None:

@@ -36,7 +36,7 @@ class _FlatAdam:
         self.m = torch.zeros_like(engine.flat_grad)
         self.v = torch.zeros_like(engine.flat_grad)
         self.step = 0
-        self._step_t = torch.tensor(0.0)   # ONE host tensor shared by every parameter's state["step"]
+        self._step_t = torch.tensor(0.0, device="cpu")   # ONE host tensor shared by every parameter's state["step"]
         for p, off in zip(engine._params, engine._offsets):
             st = optimizer.state.get(p)
             if st:  # resume from an existing torch state

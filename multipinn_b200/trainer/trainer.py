@@ -211,10 +211,23 @@ class Trainer:
             return None
         if self._fused is None:
             self._fused = FusedStep.build(self) or False
+            if self._fused is False and self._engine is not None:
+                self._explain_eager_path()
         if self._fused:
             self._fused.use_graphs = self.use_cuda_graphs
             return self._fused
         return None
+
+    def _explain_eager_path(self):
+        """Say once why this trainer stays on the eager jet path (same kernels, autograd in between; slower)."""
+        import logging
+        model = self.pinn.model
+        notes = [f"condition {i} ({getattr(c.function, '__name__', c.function)}): {c.trace_note}"
+                 for i, c in enumerate(self.pinn.conditions)
+                 if hasattr(c, "program_for") and c.program_for(model) is None and c.trace_note]
+        why = "; ".join(notes) if notes else "the loss policy, the batching or an engine option is not covered by it"
+        logging.getLogger("multipinn_b200").info("fused step not used: %s", why)
+        self.fused_step_note = why
 
     def _current_fused_step(self):
         """``fused_step()`` after following residual constants that changed since the trace (GradualTrainer's

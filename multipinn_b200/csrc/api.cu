@@ -217,8 +217,9 @@ const char* mpinn_last_error(void) { return g_err.c_str(); }
 size_t mpinn_stash_bytes(const mpinn_op_t* ops, int n_ops, int d, int order, int64_t n_points) {
   DevProg prog;
   if (build_prog(ops, n_ops, d, order, &prog)) return 0;
-  return ((size_t)prog.total_planes * (size_t)round_up64(n_points, 128) + (prog.has_skip ? kSkipScratchFloats : 0)) *
-         sizeof(float);
+  const int64_t n_pad = round_up64(n_points, 128);
+  return ((size_t)prog.total_planes * (size_t)n_pad + (prog.has_skip ? kSkipScratchFloats : 0) +
+          (size_t)wide_scratch_floats(prog, d, order, n_pad)) * sizeof(float);
 }
 
 // one private slab of n_params floats per resident CTA (at most 4 per SM on a 148-SM part)
@@ -249,13 +250,16 @@ int mpinn_pack_params(const mpinn_op_t* ops, int n_ops, const float* params, voi
   if (e != cudaSuccess) return fail_cuda("pack_params", e);
   e = launch_pack_tc(prog, params, (float*)packed, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("pack_params(tc)", e);
+  e = launch_pack_wide(prog, params, (float*)packed, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("pack_params(tc, 128-wide)", e);
   return 0;
 }
 
 static bool use_tc(const DevProg& prog, int d, int order, int engine, bool backward, int* rc) {
   *rc = 0;
   if (engine == MPINN_ENGINE_FFMA) return false;
-  const bool ok = backward ? tc_backward_supported(prog, d, order) : tc_forward_supported(prog, d, order);
+  const bool ok = (backward ? tc_backward_supported(prog, d, order) : tc_forward_supported(prog, d, order)) ||
+                  wide_supported(prog, d, order);
   if (engine == MPINN_ENGINE_TCGEN05 && !ok) {
     *rc = fail("tcgen05 engine requested but the program is not supported by it");
     return false;
@@ -284,11 +288,15 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   // stash == NULL is a value-only pass.  The tcgen05 engine has a no-stash variant for order 0 (inference) of
   // programs without skip connections (their per-CTA skip scratch lives behind the stash); otherwise ENGINE_AUTO
   // falls to the FP32-FMA engine and an explicit tcgen05 request is refused.
-  const bool tc_ok = tc && (stash != nullptr || (order == 0 && !prog.has_skip));
+  const bool wide = tc && wide_supported(prog, d, order);   // layer-wise engine: the planes ARE its working storage
+  const bool tc_ok = tc && (stash != nullptr || (order == 0 && !prog.has_skip && !wide));
   if (tc && !tc_ok && engine == MPINN_ENGINE_TCGEN05)
-    return fail("the tcgen05 engine runs without a stash buffer only at order 0 and without skip connections "
-                "(pass mpinn_stash_bytes() bytes)");
-  if (tc_ok) {
+    return fail("the tcgen05 engine runs without a stash buffer only at order 0, without skip connections and for "
+                "64-wide layers (pass mpinn_stash_bytes() bytes)");
+  if (tc_ok && wide) {
+    e = launch_fwd_wide(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad, info.sm_count,
+                        (cudaStream_t)stream);
+  } else if (tc_ok) {
     e = launch_fwd_tc(prog, params, (const float*)packed, x, n, d, order, out, (float*)stash, n_pad,
                       info.sm_count, (cudaStream_t)stream);
   } else {
@@ -329,7 +337,15 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   if (tc && dx && ops[0].kind == MPINN_OP_FOURIER)
     return fail("gradient w.r.t. the points (dx) through a Fourier-feature first op runs on the FP32-FMA engine: "
                 "request MPINN_ENGINE_FFMA for the forward AND the reverse pass (the stash layouts differ)");
-  if (tc) {
+  const bool wide = tc && wide_supported(prog, d, order);
+  if (wide && dx)
+    return fail("gradient w.r.t. the points (dx) of a 128-wide program runs on the FP32-FMA engine: request "
+                "MPINN_ENGINE_FFMA for the forward AND the reverse pass (the stash layouts differ)");
+  if (wide) {
+    // the reverse pass keeps its Zbar planes behind the stash (mpinn_stash_bytes() reserves them)
+    e = launch_bwd_wide(prog, params, (const float*)packed, x, n, d, order, dout, (float*)const_cast<void*>(stash), n_pad,
+                        (float*)workspace, slabs, n_params, dparams, info.sm_count, (cudaStream_t)stream);
+  } else if (tc) {
     e = launch_bwd_tc(prog, params, (const float*)packed, x, n, d, order, dout, (const float*)stash,
                       n_pad, (float*)workspace, slabs, n_params, dparams, dx, skip_scratch, info.sm_count,
                       (cudaStream_t)stream);
@@ -347,7 +363,7 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
 int mpinn_engine_supports(const mpinn_op_t* ops, int n_ops, int d, int order, int engine) {
   DevProg prog;
   if (build_prog(ops, n_ops, d, order, &prog)) return 0;
-  if (engine == MPINN_ENGINE_TCGEN05) return tc_forward_supported(prog, d, order) ? 1 : 0;
+  if (engine == MPINN_ENGINE_TCGEN05) return (tc_forward_supported(prog, d, order) || wide_supported(prog, d, order)) ? 1 : 0;
   return 1;   // the FP32-FMA engine runs every valid program (shared-memory budget is checked at launch)
 }
 

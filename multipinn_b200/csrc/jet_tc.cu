@@ -16,7 +16,7 @@
 
 namespace mpinn {
 
-int64_t tc_block_floats(int width) { return width == kTcW ? kTcBlockFloats : 0; }
+int64_t tc_block_floats(int width) { return width == kTcW ? kTcBlockFloats : (width == 128 ? wide_block_floats() : 0); }
 
 // optional cycle accounting of the forward kernel (build with -DMPINN_TC_TIMING=1, see jet_tc_bwd.cu): CTA 0,
 // threads 0 and 224 accumulate clock64() deltas per code segment; mpinn_debug_counters() returns them as
@@ -53,7 +53,7 @@ cudaError_t read_tc_debug_fwd(long long* out, int n) {
 __global__ void pack_tc_kernel(const __grid_constant__ DevProg prog, const float* __restrict__ params,
                                float* __restrict__ packed) {
   const DevOp& op = prog.ops[blockIdx.y];
-  if (op.kind != MPINN_OP_LINEAR || op.tc_off < 0) return;
+  if (op.kind != MPINN_OP_LINEAR || op.tc_off < 0 || op.in_dim != kTcW) return;   // 128-wide blocks: jet_tc_wide.cu
   const float* W = params + op.w_off;  // [out][in]
   char* dst = reinterpret_cast<char*>(packed + op.tc_off);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTcW * kTcW; i += gridDim.x * blockDim.x) {
@@ -83,7 +83,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ DevProg prog, const float
 
 cudaError_t launch_pack_tc(const DevProg& prog, const float* params, float* packed, cudaStream_t stream) {
   bool any = false;
-  for (int l = 0; l < prog.n_ops; ++l) any |= prog.ops[l].tc_off >= 0;
+  for (int l = 0; l < prog.n_ops; ++l) any |= prog.ops[l].tc_off >= 0 && prog.ops[l].in_dim == kTcW;
   if (!any) return cudaSuccess;
   dim3 grid(4, prog.n_ops);
   pack_tc_kernel<<<grid, 256, 0, stream>>>(prog, params, packed);

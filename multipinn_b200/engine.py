@@ -338,8 +338,8 @@ class JetEngine:
     def _engine_id(self) -> int:
         """Engine both passes of a step run on.  dL/d(points) through a Fourier-feature first op exists on the
         FP32-FMA engine only (and the two engines' stash layouts differ, so the forward must follow)."""
-        if self.points_grad and int(self.ops[0, 0]) == _lib.OP_FOURIER:
-            return _lib.ENGINE_FFMA
+        if self.points_grad and (int(self.ops[0, 0]) == _lib.OP_FOURIER or int(self.ops[0, 2]) == 128):
+            return _lib.ENGINE_FFMA      # likewise for the layer-wise 128-wide tcgen05 engine (no dx output)
         return self.kernel_engine
 
     def stash_floats(self, order: int, n: int) -> int:

@@ -72,7 +72,10 @@ def test_laplace_mode_forward_and_reverse_match_oracle(name, eng):
     out2, _ = e.forward(x, 2, need_stash=False)
     comb = sum(lap[i] * out2[1 + d + i] for i in range(d))
     assert relerr(out3[1 + d].cpu().numpy(), comb.cpu().numpy()) < TOL
-    assert relerr(out3[:1 + d].cpu().numpy(), out2[:1 + d].cpu().numpy()) < 1e-6
+    # same kernels at both orders -> identical up to rounding; a 128-wide net runs order 3 (four channels) on the layer-wise
+    # tcgen05 engine and order 2 (five channels) on the FP32-FMA engine, two roundings of the same numbers
+    same_kernels = eng == _lib.ENGINE_FFMA or e.tc_supported(2) == e.tc_supported(3)
+    assert relerr(out3[:1 + d].cpu().numpy(), out2[:1 + d].cpu().numpy()) < (1e-6 if same_kernels else TOL)
     rng = np.random.default_rng(3)
     dout_np = rng.standard_normal((n, d + 2, int(g["output_dim"]))).astype(np.float32)
     dout = torch.tensor(np.ascontiguousarray(dout_np.transpose(1, 0, 2))).cuda()

@@ -452,7 +452,14 @@ def run_ours(args):
             stash_bytes = n_domain * J_exec * hidden * 4
             hbm_peak = peaks.get("hbm_gbs", 6500.0)
             ach = flops / (bwd_ms * 1e-3) / 1e12
-            kname = f"jet_bwd_tc<{din}, {order_dom}, *>" if model.jet_engine.tc_supported(order_dom) else "jet_bwd_ffma"
+            widths = {int(r[2]) for r in model.jet_program()[:-1]}
+            if not model.jet_engine.tc_supported(order_dom):
+                kname = "jet_bwd_ffma"
+            elif widths == {128}:   # layer-wise engine (csrc/jet_tc_wide.cu): avg_launch_ms is the whole reverse SEQUENCE
+                kname = (f"layer-wise tcgen05 sequence: wide_last_bwd, then wide_wgrad_kernel<{din}, {order_dom}> + "
+                         f"wide_layer_kernel<{din}, {order_dom}, reverse> per 128x128 layer, wide_first_bwd, fold")
+            else:
+                kname = f"jet_bwd_tc<{din}, {order_dom}, *>"
             roofline = {"bound": "tensor", "kernel": f"jet reverse pass, domain condition ({kname})",
                         "achieved": ach, "peak": peak_bf16, "unit": "TFLOP/s", "frac": ach / peak_bf16,
                         "peak_source": peak_src + " (bf16 dense; the TF32 matmul peak measured in this run is "

@@ -309,6 +309,35 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
   return 0;
 }
 
+// bsum[o] = sum_pt dout[0][pt][o] in double precision (per-thread double sums, shuffle + shared-memory block reduction,
+// one double atomic per CTA and output): the last layer's bias gradient (DevProg::bsum)
+constexpr int kBsumMaxOut = 8;
+__global__ void value_seed_colsum(const float* __restrict__ dout, int64_t n, int no, double* __restrict__ bsum) {
+  double acc[kBsumMaxOut];
+#pragma unroll
+  for (int o = 0; o < kBsumMaxOut; ++o) acc[o] = 0.0;
+  for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < n; pt += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int o = 0; o < kBsumMaxOut; ++o)
+      if (o < no) acc[o] += (double)dout[pt * no + o];
+  __shared__ double red[kBsumMaxOut][8];
+#pragma unroll
+  for (int o = 0; o < kBsumMaxOut; ++o) {
+    if (o < no) {
+      double v = acc[o];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31) == 0) red[o][threadIdx.x >> 5] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < no) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+    atomicAdd(bsum + threadIdx.x, v);
+  }
+}
+
 int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, const void* packed,
                        const float* x, int64_t n, int d, int order, const float* lap_coef_host,
                        const float* dout, const void* stash, float* dparams, int64_t n_params, float* dx,
@@ -334,6 +363,24 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   int rc = 0;
   const bool tc = use_tc(prog, d, order, engine, true, &rc);
   if (rc) return rc;
+  // the last layer's bias gradient in double precision: eight doubles at the (8-byte aligned) end of the workspace,
+  // behind the slabs the engines may use
+  const DevOp& last_op = prog.ops[n_ops - 1];
+  if (last_op.kind == MPINN_OP_LINEAR && last_op.act == MPINN_ACT_NONE && !last_op.flags && last_op.b_off >= 0 &&
+      prog.n_out <= kBsumMaxOut && slabs >= 3) {
+    uintptr_t end = (reinterpret_cast<uintptr_t>(workspace) + workspace_bytes) & ~uintptr_t(7);
+    double* bsum = reinterpret_cast<double*>(end) - kBsumMaxOut;
+    slabs -= 1;   // the engines never touch the slab the sums live in
+    e = cudaMemsetAsync(bsum, 0, kBsumMaxOut * sizeof(double), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda("jet_backward (seed sum)", e);
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 2 * info.sm_count) blocks = 2 * info.sm_count;
+    value_seed_colsum<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dout, n, prog.n_out, bsum);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda("jet_backward (seed sum)", e);
+    prog.bsum = bsum;
+    prog.bsum_off = last_op.b_off;
+  }
   if (tc && dx && ops[0].kind == MPINN_OP_FOURIER)
     return fail("gradient w.r.t. the points (dx) through a Fourier-feature first op runs on the FP32-FMA engine: "
                 "request MPINN_ENGINE_FFMA for the forward AND the reverse pass (the stash layouts differ)");

@@ -31,8 +31,21 @@ struct DevProg {
   int n_ops, max_w, has_skip, d, n_out, total_planes;
   int64_t packed_floats;
   float lap_c[4];        // order 3 (Laplace mode): weights c_i of the single second-order channel sum_i c_i d2/dx_i2
+  // reverse pass only: the last layer's bias gradient is the plain column sum of the value-channel seeds, usually the
+  // largest entry of the whole gradient and a heavily cancelling sum.  api.cu sums it in double precision before
+  // the engine runs (value_seed_colsum); the engines' fold kernels take entries [bsum_off, bsum_off + n_out) from it
+  // instead of their own fp32 partials (nullptr: keep the engine's sum)
+  const double* bsum;
+  int bsum_off;
   DevOp ops[kMaxOps];
 };
+
+// fold kernels: entry i of the flat gradient comes from the double-precision seed sum when it is a last-layer bias
+__device__ __forceinline__ bool take_bsum(const double* bsum, int bsum_off, int n_out, int64_t i, float* s) {
+  if (bsum == nullptr || i < bsum_off || i >= bsum_off + n_out) return false;
+  *s = (float)bsum[i - bsum_off];
+  return true;
+}
 
 // number of jet channels: order 0/1/2 -> 1 + order*d;  order 3 (MPINN_ORDER_LAPLACE) -> value, d first derivatives, L
 // order 4 (MPINN_ORDER_HESSIAN) -> value, d first, d diagonal second and d(d-1)/2 mixed second derivatives, the

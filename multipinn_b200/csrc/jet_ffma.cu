@@ -429,11 +429,12 @@ jet_bwd_ffma(const __grid_constant__ DevProg prog, const float* __restrict__ par
 
 // dparams[i] += sum_c part[c][i]
 __global__ void fold_partials(const float* __restrict__ part, int n_slabs, int64_t n_params,
-                              float* __restrict__ dparams) {
+                              float* __restrict__ dparams, const double* __restrict__ bsum, int bsum_off, int n_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_params) return;
   float s = 0.0f;
-  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * n_params + i];
+  if (!take_bsum(bsum, bsum_off, n_out, i, &s))
+    for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * n_params + i];
   dparams[i] += s;
 }
 
@@ -486,7 +487,8 @@ static cudaError_t launch_bwd_t(const DevProg& prog, const float* params, const 
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int fb = 256;
-  fold_partials<<<(unsigned)((n_params + fb - 1) / fb), fb, 0, stream>>>(part, grid, n_params, dparams);
+  fold_partials<<<(unsigned)((n_params + fb - 1) / fb), fb, 0, stream>>>(part, grid, n_params, dparams, prog.bsum,
+                                                                          prog.bsum_off, prog.n_out);
   return cudaGetLastError();
 }
 

@@ -757,12 +757,13 @@ bool tc_backward_supported(const DevProg& prog, int d, int order) {
 
 // dparams[i] += sum_c part[c][i]  (same fold as the FFMA engine)
 __global__ void fold_partials_tc(const float* __restrict__ part, int n_slabs, int64_t n_params,
-                                 float* __restrict__ dparams) {
+                                 float* __restrict__ dparams, const double* __restrict__ bsum, int bsum_off, int n_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_params) return;
   float s = 0.0f;
   const int64_t slab = (n_params + 3) & ~int64_t(3);
-  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * slab + i];
+  if (!take_bsum(bsum, bsum_off, n_out, i, &s))
+    for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * slab + i];
   dparams[i] += s;
 }
 
@@ -785,7 +786,8 @@ static cudaError_t launch_bwd_tc_t(const DevProg& prog, const float* params, con
                                                          n_params, skip_scratch, dx, n_tiles);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  fold_partials_tc<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, dparams);
+  fold_partials_tc<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, dparams, prog.bsum,
+                                                                           prog.bsum_off, prog.n_out);
   return cudaGetLastError();
 }
 

@@ -114,6 +114,15 @@ __device__ __forceinline__ void stage_row8(uint8_t* tile, int row, int fg, const
   *reinterpret_cast<uint4*>(tile + 4 * kWdRegion + off) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
 }
 
+// the same chunk from pieces split earlier (the pipelined forward kernel splits while the previous tile's MMAs run)
+__device__ __forceinline__ void stage_pieces8(uint8_t* tile, int row, int fg, const uint32_t (&p1)[4],
+                                              const uint32_t (&p2)[4], const uint32_t (&p3)[4]) {
+  const uint32_t off = (uint32_t)(fg >> 3) * kWdRegion + (uint32_t)row * 128u + ((((uint32_t)fg & 7u) ^ ((uint32_t)row & 7u)) << 4);
+  *reinterpret_cast<uint4*>(tile + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+  *reinterpret_cast<uint4*>(tile + 2 * kWdRegion + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  *reinterpret_cast<uint4*>(tile + 4 * kWdRegion + off) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+}
+
 // D[128 x 128] = A[128 rows x 128] * B[128 x 128]^T, K-major bf16x3 tiles, smallest piece products first
 __device__ __forceinline__ void issue_wide_kmajor(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
@@ -151,6 +160,14 @@ __device__ __forceinline__ void issue_wide_mnmajor(uint32_t d_tmem, uint32_t z_t
       acc = 1;
     }
   }
+}
+
+#ifndef MPINN_WIDE_PREFETCH
+#define MPINN_WIDE_PREFETCH 1   // software pipelining of the plane loads (next tile's loads in flight under the MMAs)
+#endif
+
+__device__ __forceinline__ void l2_prefetch_bulk_w(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void copy_image(uint8_t* dst, const float* __restrict__ src) {
@@ -197,10 +214,10 @@ wide_first_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ p
 template <int D, int ORDER>
 __global__ void __launch_bounds__(kWdThreads)
 wide_first_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ x, int64_t n,
-               const float* __restrict__ zb0, float* __restrict__ part, int64_t slab_floats, int n_tiles) {
+               const float* __restrict__ zb0, float* __restrict__ part, int64_t slab_floats, int n_slabs, int n_tiles) {
   constexpr int J = jet_count(D, ORDER);
   const DevOp& op = prog.ops[0];
-  float* slab = part + (int64_t)blockIdx.x * slab_floats;
+  float* slab = part + (int64_t)(blockIdx.x % n_slabs) * slab_floats;   // HBM-bound: several CTAs per SM share the slabs
   const int p = threadIdx.x & 31, fg = threadIdx.x >> 5;
   float accw[8][D], accb[8];
 #pragma unroll
@@ -256,6 +273,10 @@ wide_last_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
   __shared__ float red[16][kWdMaxOut * J][kWdPts + 1];
   const int p = threadIdx.x & 31, fg = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#if MPINN_WIDE_PREFETCH
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
+      l2_prefetch_bulk_w(zin + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
+#endif
     float acc[kWdMaxOut][J];
 #pragma unroll
     for (int o = 0; o < kWdMaxOut; ++o)
@@ -316,6 +337,10 @@ wide_last_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
   }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t pt = tile * kWdPts + p;
+#if MPINN_WIDE_PREFETCH
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
+      l2_prefetch_bulk_w(zin + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
+#endif
     float g[kWdMaxOut][J];
 #pragma unroll
     for (int o = 0; o < kWdMaxOut; ++o)
@@ -404,14 +429,31 @@ wide_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* __re
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   uint32_t phase = 0;
+  constexpr uint32_t kTileBytes = (uint32_t)(J * kWd * kWdPts * 4);   // one tile's planes are contiguous
+  float v[J][8];
+#if MPINN_WIDE_PREFETCH
+  if (blockIdx.x < n_tiles) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(blockIdx.x, j, 8 * fg + k, p)];
+  }
+#endif
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- stage the A operand: every channel of 8 features of one point
     {
-      float v[J][8];
+#if MPINN_WIDE_PREFETCH
+      const int64_t nxt = tile + gridDim.x;
+      if (t == 0) {   // pull the tile after this one (and this tile's z planes for the epilogue) towards L2
+        if (MODE == 1) l2_prefetch_bulk_w(zprev + plane_off<J>(tile, 0, 0, 0), kTileBytes);
+        if (nxt + gridDim.x < n_tiles) l2_prefetch_bulk_w(src + plane_off<J>(nxt + gridDim.x, 0, 0, 0), kTileBytes);
+      }
+#else
 #pragma unroll
       for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(tile, j, 8 * fg + k, p)];
+#endif
       if (MODE == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -434,6 +476,17 @@ wide_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* __re
       issue_wide_kmajor(tmem, smem_u32(a_tile), smem_u32(w_tile));
       mma_commit(&bar);
     }
+#if MPINN_WIDE_PREFETCH
+    {   // the next tile's planes travel while the tensor core works
+      const int64_t nxt = tile + gridDim.x;
+      if (nxt < n_tiles) {
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(nxt, j, 8 * fg + k, p)];
+      }
+    }
+#endif
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after_sync();
@@ -482,6 +535,121 @@ wide_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* __re
   tc_fence_before_sync();
   __syncthreads();
   if (t < 32) tmem_dealloc(tmem, 128);
+}
+
+#ifndef MPINN_WIDE_PIPELINE
+#define MPINN_WIDE_PIPELINE 1   // forward layers: two accumulator blocks, the epilogue of tile i-1 and the activation
+#endif                          // jets + bf16 splitting of tile i+1 run under the MMAs of tile i
+
+// Forward of hidden op l, software-pipelined over the CTA's tiles.  Per iteration i: activation jets and bf16x3
+// pieces of tile i in registers and the plane loads of tile i+1 issued (the MMAs of tile i-1 are still running),
+// wait for those MMAs (they read the A tile), store the pieces, issue the MMAs of tile i into the other accumulator
+// block, then drain tile i-1's accumulator to its planes while they run.
+template <int D, int ORDER>
+__global__ void __launch_bounds__(kWdThreads, 1)
+wide_fwd_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* __restrict__ params,
+                      const float* __restrict__ packed, const float* __restrict__ src, float* __restrict__ dst,
+                      int n_tiles) {
+  constexpr int J = jet_count(D, ORDER);
+  constexpr uint32_t kTileBytes = (uint32_t)(J * kWd * kWdPts * 4);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* a_tile = smem;
+  uint8_t* w_tile = smem + kWdTile;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x;
+  const int p = t & 31, fg = t >> 5;
+  const int lq = fg & 3, cq = fg >> 2;
+  const DevOp& op = prog.ops[l];
+  const int act_below = prog.ops[l - 1].act;
+  if (t == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (t < 32) tmem_alloc(&tmem_base_s, 256);
+  copy_image(w_tile, packed + op.tc_off);
+  for (int i = t; i < kWdTile / 16; i += kWdThreads) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  float bias[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) bias[i] = lq == 0 ? __ldg(params + op.b_off + 32 * cq + i) : 0.0f;
+
+  auto drain = [&](int64_t tile, uint32_t block) {   // accumulator block -> planes of op l
+    if (lq < J) {
+      float acc[32];
+      tmem_ld32(tmem + block * 128u + ((uint32_t)(lq * 32) << 16) + cq * 32, acc);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[plane_off<J>(tile, lq, 32 * cq + i, p)] = acc[i] + bias[i];
+    }
+  };
+
+  float v[J][8];
+  if (blockIdx.x < n_tiles) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(blockIdx.x, j, 8 * fg + k, p)];
+  }
+  uint32_t phase = 0, it = 0;
+  int64_t prev = -1;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // ---- activation jets + bf16x3 pieces of this tile, in registers
+    uint32_t p1[J][4], p2[J][4], p3[J][4];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      float z0[J], z1[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        z0[j] = v[j][k];
+        z1[j] = v[j][k + 1];
+      }
+      act_jets<D, ORDER>(act_below, z0, prog.lap_c);
+      act_jets<D, ORDER>(act_below, z1, prog.lap_c);
+#pragma unroll
+      for (int j = 0; j < J; ++j) split_bf16x3(z0[j], z1[j], p1[j][k >> 1], p2[j][k >> 1], p3[j][k >> 1]);
+    }
+    // ---- the next tile's planes start travelling
+    const int64_t nxt = tile + gridDim.x;
+    if (nxt < n_tiles) {
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(nxt, j, 8 * fg + k, p)];
+      if (t == 0 && nxt + gridDim.x < n_tiles) l2_prefetch_bulk_w(src + plane_off<J>(nxt + gridDim.x, 0, 0, 0), kTileBytes);
+    }
+    // ---- the previous tile's MMAs read the A tile: wait for them, then overwrite it
+    if (prev >= 0) {
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) stage_pieces8(a_tile, 32 * j + p, fg, p1[j], p2[j], p3[j]);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after_sync();
+      issue_wide_kmajor(tmem + (it & 1u) * 128u, smem_u32(a_tile), smem_u32(w_tile));
+      mma_commit(&bar);
+    }
+    // ---- previous tile's accumulator -> planes, under this tile's MMAs
+    if (prev >= 0) drain(prev, (it & 1u) ^ 1u);
+    prev = tile;
+  }
+  if (prev >= 0) {
+    mbar_wait(&bar, phase);
+    tc_fence_after_sync();
+    drain(prev, (it & 1u) ^ 1u);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 256);
 }
 
 // weight / bias gradient of hidden op l:  dW_l += Zbar_l^T act_jets(z_{l-1}),  db_l += sum_p Zbar_l[0]
@@ -533,6 +701,12 @@ wide_wgrad_kernel(const __grid_constant__ DevProg prog, int l, const float* __re
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     float zb[J][8], zp[J][8];
+#if MPINN_WIDE_PREFETCH
+    if (t == 0 && tile + gridDim.x < n_tiles) {
+      l2_prefetch_bulk_w(zbar + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
+      l2_prefetch_bulk_w(zprev + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < J; ++j)
 #pragma unroll
@@ -595,11 +769,13 @@ wide_wgrad_kernel(const __grid_constant__ DevProg prog, int l, const float* __re
 
 // dparams[i] += sum_c part[c][i]
 __global__ void fold_partials_wide(const float* __restrict__ part, int n_slabs, int64_t n_params, int64_t slab_floats,
-                                   float* __restrict__ dparams) {
+                                   float* __restrict__ dparams, const double* __restrict__ bsum, int bsum_off,
+                                   int n_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_params) return;
   float s = 0.0f;
-  for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * slab_floats + i];
+  if (!take_bsum(bsum, bsum_off, n_out, i, &s))
+    for (int c = 0; c < n_slabs; ++c) s += part[(int64_t)c * slab_floats + i];
   dparams[i] += s;
 }
 
@@ -617,9 +793,18 @@ static cudaError_t fwd_wide_t(const DevProg& prog, const float* params, const fl
   const int g_cc = n_tiles < 4 * sm_count ? n_tiles : 4 * sm_count;
   wide_first_fwd<D, ORDER><<<g_cc, kWdThreads, 0, stream>>>(prog, params, x, n, stash + (int64_t)prog.ops[0].stash_plane * n_pad,
                                                            n_tiles);
+#if MPINN_WIDE_PIPELINE
+  auto kpipe = wide_fwd_layer_kernel<D, ORDER>;
+  e = cudaFuncSetAttribute(kpipe, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmem);
+  if (e != cudaSuccess) return e;
+  for (int l = 1; l < prog.n_ops - 1; ++l)
+    kpipe<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, params, packed, stash + (int64_t)prog.ops[l - 1].stash_plane * n_pad,
+                                                 stash + (int64_t)prog.ops[l].stash_plane * n_pad, n_tiles);
+#else
   for (int l = 1; l < prog.n_ops - 1; ++l)
     kern<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, params, packed, stash + (int64_t)prog.ops[l - 1].stash_plane * n_pad,
                                                 nullptr, stash + (int64_t)prog.ops[l].stash_plane * n_pad, n_tiles);
+#endif
   wide_last_fwd<D, ORDER><<<g_cc, kWdThreads, 0, stream>>>(
       prog, params, stash + (int64_t)prog.ops[prog.n_ops - 2].stash_plane * n_pad, n, out, n_tiles);
   return cudaGetLastError();
@@ -655,10 +840,12 @@ static cudaError_t bwd_wide_t(const DevProg& prog, const float* params, const fl
     kin<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, params, packed, zb[cur], zprev, zb[cur ^ 1], n_tiles);
     cur ^= 1;
   }
-  wide_first_bwd<D, ORDER><<<grid, kWdThreads, 0, stream>>>(prog, x, n, zb[cur], part, slab, n_tiles);
+  const int g_first = n_tiles < 3 * sm_count ? n_tiles : 3 * sm_count;
+  wide_first_bwd<D, ORDER><<<g_first, kWdThreads, 0, stream>>>(prog, x, n, zb[cur], part, slab, grid, n_tiles);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  fold_partials_wide<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, slab, dparams);
+  fold_partials_wide<<<(unsigned)((n_params + 255) / 256), 256, 0, stream>>>(part, grid, n_params, slab, dparams, prog.bsum,
+                                                                             prog.bsum_off, prog.n_out);
   return cudaGetLastError();
 }
 

@@ -1,7 +1,9 @@
 """One forward + reverse pass of the burgers network (4x128) on the layer-wise tcgen05 engine; run under
 `ncu --metrics gpu__time_duration.sum` for the per-kernel durations, or plain for CUDA-event totals."""
+import os
 import sys
 import torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import multipinn_b200 as mp
 from multipinn_b200 import _lib
 

@@ -652,6 +652,130 @@ wide_fwd_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* 
   if (t < 32) tmem_dealloc(tmem, 256);
 }
 
+// Input gradient of hidden op l (gin = Zbar_l, gout = Zbar_{l-1}), reordered so that the expensive part of a tile's
+// epilogue -- the activation's reverse and the plane stores -- runs under the NEXT tile's MMAs: the accumulator is
+// exchanged through the A tile (channel-major lanes -> all channels of a (point, feature) in one thread) into
+// registers first, then the next tile is staged and issued, then the registers are worked off.
+template <int D, int ORDER>
+__global__ void __launch_bounds__(kWdThreads, 1)
+wide_dgrad_layer_kernel(const __grid_constant__ DevProg prog, int l, const float* __restrict__ packed,
+                        const float* __restrict__ src, const float* __restrict__ zprev, float* __restrict__ dst,
+                        int n_tiles) {
+  constexpr int J = jet_count(D, ORDER);
+  constexpr uint32_t kTileBytes = (uint32_t)(J * kWd * kWdPts * 4);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* a_tile = smem;
+  uint8_t* w_tile = smem + kWdTile;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x;
+  const int p = t & 31, fg = t >> 5;
+  const int lq = fg & 3, cq = fg >> 2;
+  const DevOp& op = prog.ops[l];
+  const int act_below = prog.ops[l - 1].act;
+  if (t == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (t < 32) tmem_alloc(&tmem_base_s, 128);
+  copy_image(w_tile, packed + op.tc_off + kWdTile / 4);
+  for (int i = t; i < kWdTile / 16; i += kWdThreads) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  float v[J][8];
+  // ---- prologue: stage and issue the CTA's first tile
+  if (blockIdx.x < n_tiles) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(blockIdx.x, j, 8 * fg + k, p)];
+#pragma unroll
+    for (int j = 0; j < J; ++j) stage_row8(a_tile, 32 * j + p, fg, v[j]);
+    if (t == 0) {
+      l2_prefetch_bulk_w(zprev + plane_off<J>(blockIdx.x, 0, 0, 0), kTileBytes);
+      if (blockIdx.x + gridDim.x < n_tiles) l2_prefetch_bulk_w(src + plane_off<J>(blockIdx.x + gridDim.x, 0, 0, 0), kTileBytes);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (t == 0 && blockIdx.x < n_tiles) {
+    issue_wide_kmajor(tmem, smem_u32(a_tile), smem_u32(w_tile));
+    mma_commit(&bar);
+  }
+  uint32_t phase = 0;
+  float* X = reinterpret_cast<float*>(a_tile);   // exchange buffer [feature][row]; the A tile is free once the MMAs are done
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t nxt = tile + gridDim.x;
+    const bool more = nxt < n_tiles;
+    if (t == 0 && more) {
+      l2_prefetch_bulk_w(zprev + plane_off<J>(nxt, 0, 0, 0), kTileBytes);
+      if (nxt + gridDim.x < n_tiles) l2_prefetch_bulk_w(src + plane_off<J>(nxt + gridDim.x, 0, 0, 0), kTileBytes);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after_sync();
+    if (lq < J) {
+      float acc[32];
+      tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + cq * 32, acc);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) X[(32 * cq + i) * 128 + 32 * lq + p] = acc[i];
+    }
+    if (more) {   // the next tile's Zbar planes travel while the exchange completes
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = src[plane_off<J>(nxt, j, 8 * fg + k, p)];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    float ab[J][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < J; ++j) ab[j][k] = X[(8 * fg + k) * 128 + 32 * j + p];
+    __syncthreads();   // X consumed: the A tile may be overwritten
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) stage_row8(a_tile, 32 * j + p, fg, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[j][k] = zprev[plane_off<J>(tile, j, 8 * fg + k, p)];
+    if (more) {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (t == 0) {
+        tc_fence_after_sync();
+        issue_wide_kmajor(tmem, smem_u32(a_tile), smem_u32(w_tile));
+        mma_commit(&bar);
+      }
+    }
+    // ---- activation reverse + plane stores of this tile, under the next tile's MMAs
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z[J], g[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        z[j] = v[j][k];
+        g[j] = ab[j][k];
+      }
+      act_jets_bwd<D, ORDER>(act_below, z, g, prog.lap_c);
+#pragma unroll
+      for (int j = 0; j < J; ++j) dst[plane_off<J>(tile, j, 8 * fg + k, p)] = g[j];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 128);
+}
+
 // weight / bias gradient of hidden op l:  dW_l += Zbar_l^T act_jets(z_{l-1}),  db_l += sum_p Zbar_l[0]
 template <int D, int ORDER>
 __global__ void __launch_bounds__(kWdThreads, 1)
@@ -829,6 +953,9 @@ static cudaError_t bwd_wide_t(const DevProg& prog, const float* params, const fl
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmem);
   if (e != cudaSuccess) return e;
+  auto kdg = wide_dgrad_layer_kernel<D, ORDER>;
+  e = cudaFuncSetAttribute(kdg, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmem);
+  if (e != cudaSuccess) return e;
   float* zb[2] = {stash + (int64_t)prog.total_planes * n_pad, stash + ((int64_t)prog.total_planes + J * kWd) * n_pad};
   const int L = prog.n_ops;
   int cur = 0;
@@ -837,7 +964,11 @@ static cudaError_t bwd_wide_t(const DevProg& prog, const float* params, const fl
   for (int l = L - 2; l >= 1; --l) {
     const float* zprev = stash + (int64_t)prog.ops[l - 1].stash_plane * n_pad;
     kw<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, zb[cur], zprev, part, slab, n_tiles);
+#if MPINN_WIDE_PIPELINE
+    kdg<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, packed, zb[cur], zprev, zb[cur ^ 1], n_tiles);
+#else
     kin<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, params, packed, zb[cur], zprev, zb[cur ^ 1], n_tiles);
+#endif
     cur ^= 1;
   }
   const int g_first = n_tiles < 3 * sm_count ? n_tiles : 3 * sm_count;

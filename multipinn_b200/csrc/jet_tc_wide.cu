@@ -262,7 +262,7 @@ wide_first_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ x
 }
 
 // out[j][pt][o] = sum_f Wl[o][f] act_jets(z)[j][f] + b[o] (j = 0)
-template <int D, int ORDER>
+template <int D, int ORDER, int NO>   // NO: compile-time bound of the output count (1 or kWdMaxOut)
 __global__ void __launch_bounds__(kWdThreads)
 wide_last_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ params, const float* __restrict__ zin,
               int64_t n, float* __restrict__ out, int n_tiles) {
@@ -270,27 +270,32 @@ wide_last_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
   const DevOp& op = prog.ops[prog.n_ops - 1];
   const int act = prog.ops[prog.n_ops - 2].act;
   const int no = op.out_dim;
-  __shared__ float red[16][kWdMaxOut * J][kWdPts + 1];
+  __shared__ float red[16][NO * J][kWdPts + 1];
   const int p = threadIdx.x & 31, fg = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #if MPINN_WIDE_PREFETCH
     if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
       l2_prefetch_bulk_w(zin + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
 #endif
-    float acc[kWdMaxOut][J];
+    float acc[NO][J];
 #pragma unroll
-    for (int o = 0; o < kWdMaxOut; ++o)
+    for (int o = 0; o < NO; ++o)
 #pragma unroll
       for (int j = 0; j < J; ++j) acc[o][j] = 0.0f;
+    float zv[J][8];   // all of the tile's loads in flight at once
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zv[j][k] = zin[plane_off<J>(tile, j, 8 * fg + k, p)];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int f = 8 * fg + k;
       float z[J];
 #pragma unroll
-      for (int j = 0; j < J; ++j) z[j] = zin[plane_off<J>(tile, j, f, p)];
+      for (int j = 0; j < J; ++j) z[j] = zv[j][k];
       act_jets<D, ORDER>(act, z, prog.lap_c);
 #pragma unroll
-      for (int o = 0; o < kWdMaxOut; ++o) {
+      for (int o = 0; o < NO; ++o) {
         if (o < no) {
           const float w = __ldg(params + op.w_off + o * kWd + f);
 #pragma unroll
@@ -300,7 +305,7 @@ wide_last_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
     }
     __syncthreads();   // previous tile's readers are done
 #pragma unroll
-    for (int o = 0; o < kWdMaxOut; ++o)
+    for (int o = 0; o < NO; ++o)
 #pragma unroll
       for (int j = 0; j < J; ++j) red[fg][o * J + j][p] = acc[o][j];
     __syncthreads();
@@ -317,20 +322,20 @@ wide_last_fwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
 }
 
 // reverse of the last layer: Zbar of the last hidden op (written to zb), dWl, dbl
-template <int D, int ORDER>
+template <int D, int ORDER, int NO>
 __global__ void __launch_bounds__(kWdThreads)
 wide_last_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ params, const float* __restrict__ zin,
               const float* __restrict__ dout, int64_t n, float* __restrict__ zb, float* __restrict__ part,
-              int64_t slab_floats, int n_tiles) {
+              int64_t slab_floats, int n_slabs, int n_tiles) {
   constexpr int J = jet_count(D, ORDER);
   const DevOp& op = prog.ops[prog.n_ops - 1];
   const int act = prog.ops[prog.n_ops - 2].act;
   const int no = op.out_dim;
-  float* slab = part + (int64_t)blockIdx.x * slab_floats;
+  float* slab = part + (int64_t)(blockIdx.x % n_slabs) * slab_floats;   // CTAs beyond the slab count share (atomics)
   const int p = threadIdx.x & 31, fg = threadIdx.x >> 5;
-  float accw[kWdMaxOut][8], accb[kWdMaxOut];
+  float accw[NO][8], accb[NO];
 #pragma unroll
-  for (int o = 0; o < kWdMaxOut; ++o) {
+  for (int o = 0; o < NO; ++o) {
     accb[o] = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) accw[o][k] = 0.0f;
@@ -341,26 +346,31 @@ wide_last_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
     if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
       l2_prefetch_bulk_w(zin + plane_off<J>(tile + gridDim.x, 0, 0, 0), (uint32_t)(J * kWd * kWdPts * 4));
 #endif
-    float g[kWdMaxOut][J];
+    float g[NO][J];
 #pragma unroll
-    for (int o = 0; o < kWdMaxOut; ++o)
+    for (int o = 0; o < NO; ++o)
 #pragma unroll
       for (int j = 0; j < J; ++j) g[o][j] = (o < no && pt < n) ? dout[((int64_t)j * n + pt) * no + o] : 0.0f;
 #pragma unroll
-    for (int o = 0; o < kWdMaxOut; ++o) accb[o] += g[o][0];
+    for (int o = 0; o < NO; ++o) accb[o] += g[o][0];
+    float zv[J][8];   // all of the tile's loads in flight at once
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zv[j][k] = zin[plane_off<J>(tile, j, 8 * fg + k, p)];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int f = 8 * fg + k;
       float z[J], a[J], ab[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        z[j] = zin[plane_off<J>(tile, j, f, p)];
+        z[j] = zv[j][k];
         a[j] = z[j];
         ab[j] = 0.0f;
       }
       act_jets<D, ORDER>(act, a, prog.lap_c);
 #pragma unroll
-      for (int o = 0; o < kWdMaxOut; ++o) {
+      for (int o = 0; o < NO; ++o) {
         if (o < no) {
           const float w = __ldg(params + op.w_off + o * kWd + f);
 #pragma unroll
@@ -376,7 +386,7 @@ wide_last_bwd(const __grid_constant__ DevProg prog, const float* __restrict__ pa
     }
   }
 #pragma unroll
-  for (int o = 0; o < kWdMaxOut; ++o) {
+  for (int o = 0; o < NO; ++o) {
     if (o < no) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -929,8 +939,12 @@ static cudaError_t fwd_wide_t(const DevProg& prog, const float* params, const fl
     kern<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, params, packed, stash + (int64_t)prog.ops[l - 1].stash_plane * n_pad,
                                                 nullptr, stash + (int64_t)prog.ops[l].stash_plane * n_pad, n_tiles);
 #endif
-  wide_last_fwd<D, ORDER><<<g_cc, kWdThreads, 0, stream>>>(
-      prog, params, stash + (int64_t)prog.ops[prog.n_ops - 2].stash_plane * n_pad, n, out, n_tiles);
+  if (prog.n_out == 1)
+    wide_last_fwd<D, ORDER, 1><<<g_cc, kWdThreads, 0, stream>>>(
+        prog, params, stash + (int64_t)prog.ops[prog.n_ops - 2].stash_plane * n_pad, n, out, n_tiles);
+  else
+    wide_last_fwd<D, ORDER, kWdMaxOut><<<g_cc, kWdThreads, 0, stream>>>(
+        prog, params, stash + (int64_t)prog.ops[prog.n_ops - 2].stash_plane * n_pad, n, out, n_tiles);
   return cudaGetLastError();
 }
 
@@ -959,8 +973,14 @@ static cudaError_t bwd_wide_t(const DevProg& prog, const float* params, const fl
   float* zb[2] = {stash + (int64_t)prog.total_planes * n_pad, stash + ((int64_t)prog.total_planes + J * kWd) * n_pad};
   const int L = prog.n_ops;
   int cur = 0;
-  wide_last_bwd<D, ORDER><<<grid, kWdThreads, 0, stream>>>(prog, params, stash + (int64_t)prog.ops[L - 2].stash_plane * n_pad,
-                                                          dout, n, zb[cur], part, slab, n_tiles);
+  if (prog.n_out == 1) {   // 64 registers: two CTAs per SM
+    const int g_last = n_tiles < 2 * sm_count ? n_tiles : 2 * sm_count;
+    wide_last_bwd<D, ORDER, 1><<<g_last, kWdThreads, 0, stream>>>(prog, params, stash + (int64_t)prog.ops[L - 2].stash_plane * n_pad,
+                                                                 dout, n, zb[cur], part, slab, grid, n_tiles);
+  } else {
+    wide_last_bwd<D, ORDER, kWdMaxOut><<<grid, kWdThreads, 0, stream>>>(
+        prog, params, stash + (int64_t)prog.ops[L - 2].stash_plane * n_pad, dout, n, zb[cur], part, slab, grid, n_tiles);
+  }
   for (int l = L - 2; l >= 1; --l) {
     const float* zprev = stash + (int64_t)prog.ops[l - 1].stash_plane * n_pad;
     kw<<<grid, kWdThreads, kWdSmem, stream>>>(prog, l, zb[cur], zprev, part, slab, n_tiles);

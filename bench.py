@@ -457,7 +457,7 @@ def run_ours(args):
                 kname = "jet_bwd_ffma"
             elif widths == {128}:   # layer-wise engine (csrc/jet_tc_wide.cu): avg_launch_ms is the whole reverse SEQUENCE
                 kname = (f"layer-wise tcgen05 sequence: wide_last_bwd, then wide_wgrad_kernel<{din}, {order_dom}> + "
-                         f"wide_layer_kernel<{din}, {order_dom}, reverse> per 128x128 layer, wide_first_bwd, fold")
+                         f"wide_dgrad_layer_kernel<{din}, {order_dom}> per 128x128 layer, wide_first_bwd, fold")
             else:
                 kname = f"jet_bwd_tc<{din}, {order_dom}, *>"
             roofline = {"bound": "tensor", "kernel": f"jet reverse pass, domain condition ({kname})",
@@ -486,6 +486,17 @@ def run_ours(args):
                         # traffic, ~1000x that (stash_bytes_per_launch written once and read once)
                         "algorithmic_hbm_bytes_per_step": sum(len(p) for p in dev_pts) * din * 4 * 2
                         + 3 * sum(p.numel() for p in model.parameters()) * 4}
+            if "layer-wise" in kname:
+                # layer-wise engine: every layer pass reads / writes whole plane sets (J_exec x 128 x 4 B per point);
+                # forward 1 + 2 per square layer + 1, reverse 2 + 5 per square layer + 1
+                n_sq = len(model.jet_program()) - 2
+                plane = n_domain * J_exec * 128 * 4
+                roofline["design_plane_bytes_forward"] = (2 + 2 * n_sq) * plane
+                roofline["design_plane_bytes_reverse"] = (3 + 5 * n_sq) * plane
+                roofline["hbm_frac_forward"] = ((2 + 2 * n_sq) * plane / (fwd_ms * 1e-3) / 1e9 / hbm_peak) if fwd_ms else None
+                roofline["hbm_frac_reverse"] = (3 + 5 * n_sq) * plane / (bwd_ms * 1e-3) / 1e9 / hbm_peak
+                roofline["note"] = ("HBM-bound by design: hbm_frac_* = plane bytes the layer-wise kernels must move "
+                                    "/ time / measured HBM peak; frac (tensor) is against the algorithmic flops")
             tr_b, tr_f = roofline["traffic"], roofline["fwd_traffic"]
             roofline["measured_dram_bytes_domain_fwd_plus_bwd"] = (tr_b + tr_f) if (tr_b and tr_f) else None
         step_flops = 0

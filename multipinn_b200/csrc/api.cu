@@ -312,7 +312,8 @@ int mpinn_jet_forward(const mpinn_op_t* ops, int n_ops, const float* params, con
 // bsum[o] = sum_pt dout[0][pt][o] in double precision (per-thread double sums, shuffle + shared-memory block reduction,
 // one double atomic per CTA and output): the last layer's bias gradient (DevProg::bsum)
 constexpr int kBsumMaxOut = 8;
-__global__ void value_seed_colsum(const float* __restrict__ dout, int64_t n, int no, double* __restrict__ bsum) {
+__global__ void value_seed_colsum(const float* __restrict__ dout, int64_t n, int no, double* __restrict__ bsum,
+                                  int single_cta) {
   double acc[kBsumMaxOut];
 #pragma unroll
   for (int o = 0; o < kBsumMaxOut; ++o) acc[o] = 0.0;
@@ -334,7 +335,8 @@ __global__ void value_seed_colsum(const float* __restrict__ dout, int64_t n, int
   if (threadIdx.x < no) {
     double v = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
-    atomicAdd(bsum + threadIdx.x, v);
+    if (single_cta) bsum[threadIdx.x] = v;   // small launches: one CTA, no memset node in front
+    else atomicAdd(bsum + threadIdx.x, v);
   }
 }
 
@@ -371,11 +373,13 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
     uintptr_t end = (reinterpret_cast<uintptr_t>(workspace) + workspace_bytes) & ~uintptr_t(7);
     double* bsum = reinterpret_cast<double*>(end) - kBsumMaxOut;
     slabs -= 1;   // the engines never touch the slab the sums live in
-    e = cudaMemsetAsync(bsum, 0, kBsumMaxOut * sizeof(double), (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail_cuda("jet_backward (seed sum)", e);
     int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
     if (blocks > 2 * info.sm_count) blocks = 2 * info.sm_count;
-    value_seed_colsum<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dout, n, prog.n_out, bsum);
+    if (blocks > 1) {
+      e = cudaMemsetAsync(bsum, 0, kBsumMaxOut * sizeof(double), (cudaStream_t)stream);
+      if (e != cudaSuccess) return fail_cuda("jet_backward (seed sum)", e);
+    }
+    value_seed_colsum<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dout, n, prog.n_out, bsum, blocks == 1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda("jet_backward (seed sum)", e);
     prog.bsum = bsum;

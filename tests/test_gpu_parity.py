@@ -458,3 +458,27 @@ def test_sumsq_kernel(cuda_backend, n, stride):
     cuda_backend.sumsq(r, acc)
     ref = float(torch.sum(r.double() ** 2))
     assert abs(acc.item() - ref) / ref < 1e-5
+
+
+# ------------------------------------------------------------------------------ last-layer bias gradient
+@pytest.mark.parametrize("eng", ENGINES, ids=ENGINE_IDS)
+@pytest.mark.parametrize("n", [700, 5000, 70001])
+def test_last_layer_bias_gradient_is_summed_in_double(n, eng):
+    """dL/db of the last layer is the column sum of the value-channel seeds, usually the largest entry of the flat
+    gradient (reference: loss.backward(), trainer/trainer.py:141).  csrc/api.cu sums it in double precision before
+    the engine runs (value_seed_colsum; one CTA without atomics for small launches, double atomics otherwise), so it
+    is exact to fp32 rounding even for seeds that cancel to 1e-4 of their magnitude, and identical from run to run."""
+    m, din, dout_dim = full_model("poisson_2D_1C", 3, eng)
+    e = m.jet_engine
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.rand((n, din), device="cuda", generator=g)
+    out, stash = e.forward(x, 1, need_stash=True)
+    dout = torch.randn(out.shape, device="cuda", generator=g) * 100.0
+    dout[0] -= dout[0].mean(dim=0, keepdim=True) * (1.0 - 1e-4)          # heavy cancellation in the column sum
+    exact = dout[0].double().sum(dim=0).cpu().numpy()
+    off = sum(p.numel() for p in list(m.parameters())[:-1])
+    g1 = e.backward(x, 1, dout, stash).cpu().numpy().copy()
+    g2 = e.backward(x, 1, dout, stash).cpu().numpy().copy()
+    got = g1[off:off + dout_dim].astype(np.float64)
+    assert np.all(np.abs(got - exact) <= 1.2e-7 * np.abs(exact) + 1e-30), (got, exact)
+    assert np.array_equal(g1[off:off + dout_dim], g2[off:off + dout_dim])

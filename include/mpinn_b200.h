@@ -87,7 +87,10 @@ int mpinn_jet_forward(const mpinn_op_t* ops_host, int n_ops, const float* params
 /* Reverse pass: parameter gradient of a scalar loss given dL/d(out jets).
  * Replaces `loss.backward()` through the double-backward graph (reference trainer/trainer.py:141).
  *   dout    [J,n,o]  gradient w.r.t. the forward's `out`
- *   dparams [P]      ACCUMULATED into (+=); P = number of floats in `params`
+ *   dparams [P]      ACCUMULATED into (+=); P = number of floats in `params`.  The last layer's bias entries (the
+ *                    column sums of dout[0], usually the largest entries of the gradient) are summed in double
+ *                    precision and are identical from run to run; the rest is fp32 with per-CTA partial slabs
+ *   workspace        mpinn_backward_workspace_bytes() bytes (partial slabs; its last 64 bytes hold those sums)
  *   dx      [n,d]    written if non-NULL (gradient w.r.t. the points: the `points.grad` the reference's
  *                    `batch_loss.backward()` leaves behind), else skipped; with a FOURIER first op on the FP32-FMA
  *                    engine only (forward and reverse with MPINN_ENGINE_FFMA: the tcgen05 reverse kernel refuses it) */

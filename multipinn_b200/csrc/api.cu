@@ -369,10 +369,14 @@ int mpinn_jet_backward(const mpinn_op_t* ops, int n_ops, const float* params, co
   // behind the slabs the engines may use
   const DevOp& last_op = prog.ops[n_ops - 1];
   if (last_op.kind == MPINN_OP_LINEAR && last_op.act == MPINN_ACT_NONE && !last_op.flags && last_op.b_off >= 0 &&
-      prog.n_out <= kBsumMaxOut && slabs >= 3) {
+      prog.n_out <= kBsumMaxOut) {
+    // slabs the sums (plus alignment slack) may overlap: more than one for very small networks
+    const size_t slab_bytes = (size_t)n_params * sizeof(float);
+    const int reserve = (int)((kBsumMaxOut * sizeof(double) + 8 + slab_bytes - 1) / slab_bytes) + 1;
+    if (slabs < reserve + 2) return fail("backward workspace too small");
     uintptr_t end = (reinterpret_cast<uintptr_t>(workspace) + workspace_bytes) & ~uintptr_t(7);
     double* bsum = reinterpret_cast<double*>(end) - kBsumMaxOut;
-    slabs -= 1;   // the engines never touch the slab the sums live in
+    slabs -= reserve;   // the engines never touch the slabs the sums live in
     int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
     if (blocks > 2 * info.sm_count) blocks = 2 * info.sm_count;
     if (blocks > 1) {
